@@ -1,0 +1,154 @@
+/*
+ * triad_b200 — C ABI of the B200-native max-mean similarity + symmetric InfoNCE path.
+ *
+ * The reference (SajayR/TRIAD) is pure Python and has NO FFI of its own: the boundary it
+ * exposes for this path is the set of methods in src/model.py / src/retrieval.py listed in
+ * SURVEY.md §8(b).  The entry points below are what a ctypes binding behind those methods
+ * calls (INTEGRATION.md shows the stub); each one cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (torch storage); the library
+ *     never allocates device memory — scratch is passed in (`ws`, sized by *_workspace_bytes);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; 0 = default);
+ *   - return value: 0 on success, a negative TRIAD_ERR_* otherwise; nothing throws;
+ *   - tensors are contiguous row-major; q/v need 16-byte aligned base pointers and D % 8 == 0;
+ *   - `temperature` is a device pointer to one fp32 (the nn.Parameter at model.py:348), so no
+ *     host synchronisation is needed to read it; it must be > 0;
+ *   - M = Bq*Nq is the number of query-token rows ("rows" below).
+ *
+ * Layouts the library defines (the reference never materialises them on this path):
+ *   idx   : [Bv][M]  uint8 when Nv <= 256 else uint16 — idx[j][i*Nq+a] = argmax_p S[i,j,a,p],
+ *           first index among ties (torch.max, model.py:389).  image-major so that one
+ *           128-row tile writes 128 contiguous bytes and the dV pass reads one image's
+ *           winners contiguously.
+ *   row_scale : [M] fp32 — weight of token row r in its query's (masked) mean:
+ *           1/Nq (model.py:391) or mask/clamp(sum mask,1e-7) (model.py:509-512).
+ */
+#ifndef TRIAD_B200_H
+#define TRIAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRIAD_OK                 0
+#define TRIAD_ERR_BAD_ARG       (-1)  /* null pointer / negative size / unknown enum          */
+#define TRIAD_ERR_BAD_SHAPE     (-2)  /* D % 8 != 0, Nv > 65535, B == 0, ...                  */
+#define TRIAD_ERR_ALIGNMENT     (-3)  /* q / v / ws not 16-byte aligned                       */
+#define TRIAD_ERR_WORKSPACE     (-4)  /* ws_bytes smaller than *_workspace_bytes()            */
+#define TRIAD_ERR_CUDA          (-5)  /* a CUDA runtime/driver call failed (see last_error)   */
+#define TRIAD_ERR_ARCH          (-6)  /* device is not sm_100 (the kernels are sm_100a only)  */
+#define TRIAD_ERR_UNSUPPORTED   (-7)  /* shape outside what this build implements             */
+#define TRIAD_ERR_TIMEOUT       (-8)  /* a kernel watchdog fired (pipeline deadlock guard)    */
+
+#define TRIAD_DTYPE_F32   0
+#define TRIAD_DTYPE_BF16  1
+
+/* flags for triad_maxmean_fwd */
+#define TRIAD_FWD_DEFAULT      0
+#define TRIAD_FWD_FORCE_SIMT   1   /* fp32-accumulate CUDA-core kernel (always used for fp32 inputs) */
+#define TRIAD_FWD_FORCE_1CTA   2   /* tcgen05 kernel with cta_group::1 (debug / small shapes)        */
+#define TRIAD_FWD_DIVIDE_BY_T  4   /* S = <q,v> / T (retrieval.py:108) instead of <q,v> * T          */
+
+int         triad_abi_version(void);
+const char* triad_status_string(int status);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char* triad_last_error(void);
+/* 0 if `device` can run the kernels (compute capability 10.x), TRIAD_ERR_ARCH otherwise. */
+int         triad_device_check(int device);
+
+/* ---- row weights ------------------------------------------------------------------- */
+/* row_scale[i*Nq+t] = mask ? mask[i,t]/clamp(sum_t mask[i,t],1e-7) : 1/Nq.
+ * Replaces model.py:391 (mean) and model.py:509-512 (mask.float(), sum, clamp, divide).
+ * `mask` is the tokenizer's int64 attention mask [Bq,Nq] (model.py:118) or NULL. */
+int triad_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, void* stream);
+
+/* ---- forward: token similarity -> max over patches -> weighted mean over tokens ------ */
+/* Replaces compute_all_similarities_av (model.py:370-392) and _tv (model.py:490-514):
+ *   S[i,j,a,p] = round(T * <q[i,a,:], v[j,p,:]>)   (rounded like the reference: see triad_round.h)
+ *   clip[i,j]  = sum_a row_scale[i*Nq+a] * max_p S[i,j,a,p]
+ * q [Bq,Nq,D], v [Bv,Nv,D] in `dtype`; clip fp32 [Bq,Bv]; idx as described above or NULL
+ * (forward-only).  The Bq x Bv x Nq x Nv tensor is never written to memory. */
+size_t triad_maxmean_fwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
+int triad_maxmean_fwd(const void* q, const void* v, const float* row_scale,
+                      const float* temperature,
+                      int Bq, int Bv, int Nq, int Nv, int D, int dtype,
+                      float* clip, void* idx,
+                      void* ws, size_t ws_bytes, int flags, void* stream);
+
+/* Debug/test aid: synchronises `stream` and returns TRIAD_ERR_TIMEOUT if the forward kernel
+ * that last used `ws` tripped its pipeline-deadlock watchdog, TRIAD_OK otherwise. */
+int triad_maxmean_fwd_status(const void* ws, void* stream);
+
+/* ---- symmetric InfoNCE on a row block of the clip matrix ---------------------------- */
+/* Replaces model.py:453-459 / :572-578 (two log_softmax + gathers) and the statistics block
+ * model.py:435-450 / :553-568, for rows [row0,row0+rows) of a B x B matrix (rows == B and
+ * row0 == 0 on one GPU; one block per rank when the batch is row-sharded).
+ *
+ * Step 1 (per rank): row log-sum-exp and this block's per-column (max, sum exp) partials.
+ *   row_lse  fp32 [rows];  col_part fp32 [2][B]  (col_part[0]=running max, [1]=sum exp(x-max))
+ *   ws: triad_infonce_workspace_bytes(rows,B) (shared with step 2). */
+int triad_infonce_partial(const float* clip_rows, int rows, int B, int row0,
+                          float* row_lse, float* col_part,
+                          void* ws, size_t ws_bytes, void* stream);
+/* Step 2: given the column partials of all `nparts` row blocks (concatenated [nparts][2][B];
+ * an all-gather of step 1's col_part), produce
+ *   g     fp32 [rows,B] : dLoss/dclip = (softmax_row + softmax_col - 2 I)/(2B) * grad_scale
+ *   sums  fp64 [8]      : {sum_i(row_lse-diag) + sum_{j in block}(col_lse-diag),  sum diag,
+ *                          sum diag^2, sum offdiag, sum offdiag^2, max offdiag,
+ *                          sum g*clip (unscaled), 0}   — block-local, to be summed (max for [5])
+ *                          across ranks; loss = sums[0]/(2B).
+ * ws: triad_infonce_workspace_bytes(rows,B). */
+size_t triad_infonce_workspace_bytes(int rows, int B);
+int triad_infonce_finish(const float* clip_rows, int rows, int B, int row0,
+                         const float* row_lse, const float* col_parts, int nparts,
+                         float grad_scale, float* g, double* sums,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ---- backward through max-mean ------------------------------------------------------- */
+/* Replaces autograd's backward of model.py:387-391:
+ *   dq[i,a,:] = T*row_scale[r] * sum_j g[i,j] * v[j, idx[j][r], :]
+ *   dv[j,p,:] = sum_{r: idx[j][r]==p} T*row_scale[r]*g[i(r),j] * q[r,:]
+ *   dT        = sum_ij g[i,j]*clip[i,j] / T
+ * g fp32 [Bq,Bv] is dLoss/dclip.  dq is written in `dtype` ([Bq,Nq,D]); dv is written as
+ * fp32 [Bv,Nv,D] when dv_f32 != 0 (partial to be reduce-scattered across ranks) else in
+ * `dtype`; dT fp32 [1].  Any of dq / dv / dT may be NULL to skip it. */
+size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
+int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
+                      const float* clip, const float* row_scale, const float* temperature,
+                      int Bq, int Bv, int Nq, int Nv, int D, int dtype,
+                      void* dq, void* dv, int dv_f32, float* dT,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---- retrieval: one query against a gallery, top-k ---------------------------------- */
+/* Replaces the per-pair aggregators retrieval.py:106-110 / :190-193 (direction 0:
+ * mean_q max_p) and :112-115 / :195-198 (direction 1: mean_p max_q) and the python double
+ * loops at :161-175 / :265-279: scores[n] for n in [0,n_img), each image Nv patches.
+ * The retrieval path DIVIDES by the temperature (retrieval.py:108); `divide_by_T` selects
+ * that (1) or the training-time multiply (0).  scores fp32 [n_img]. */
+size_t triad_retrieve_workspace_bytes(int Nq, int n_img, int Nv, int D, int dtype);
+int triad_retrieve_scores(const void* q, int Nq, const void* gallery, int n_img, int Nv, int D,
+                          int dtype, const float* temperature, int divide_by_T, int direction,
+                          float* scores, void* ws, size_t ws_bytes, void* stream);
+/* top-k of scores (descending, ties -> lower id first, like a stable argsort of -scores):
+ * out_scores fp32 [k], out_ids int32 [k].  ws: triad_topk_workspace_bytes(n). */
+size_t triad_topk_workspace_bytes(int n, int k);
+int triad_topk(const float* scores, int n, int k, float* out_scores, int32_t* out_ids,
+               void* ws, size_t ws_bytes, void* stream);
+/* rank of the diagonal in each row of an N x N similarity matrix (retrieval.py:125-133):
+ * ranks int32 [N] = #{j : sim[i,j] > sim[i,i]} + #{j < i : sim[i,j] == sim[i,i]}. */
+int triad_diag_ranks(const float* sim, int N, int32_t* ranks, void* stream);
+
+/* ---- per-pair normalised similarity (viz / forward()) -------------------------------- */
+/* Replaces compute_similarity_matrix (model.py:355-368): out[b,n1,n2] =
+ * T * <f1[b,n1]/|f1[b,n1]|, f2[b,n2]/|f2[b,n2]|>, fp32 in/out. */
+int triad_similarity_matrix(const float* f1, const float* f2, const float* temperature,
+                            int B, int N1, int N2, int D, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIAD_B200_H */

@@ -1,0 +1,100 @@
+// Shared declarations for the triad_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/triad_b200.h"
+#include "triad_round.h"
+
+namespace triad {
+
+int cuda_fail(cudaError_t e, const char* where);   // records triad_last_error(), returns TRIAD_ERR_CUDA
+int fail_msg(int status, const char* msg);
+
+#define TRIAD_CUDA_CHECK(expr)                                              \
+    do {                                                                    \
+        cudaError_t e__ = (expr);                                           \
+        if (e__ != cudaSuccess) return ::triad::cuda_fail(e__, #expr);      \
+    } while (0)
+
+#define TRIAD_LAUNCH_CHECK(what)                                            \
+    do {                                                                    \
+        cudaError_t e__ = cudaGetLastError();                               \
+        if (e__ != cudaSuccess) return ::triad::cuda_fail(e__, what);       \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- forward partial-sum layout ---------------------------------------------------------
+// The forward kernels reduce row maxima per 32-row GROUP (one warp of the epilogue) and per
+// query inside the group, deterministically (shuffle tree), into
+//     part[j][g][s]   j < Bv, g < G = ceil(M/32), s < S = 31/Nq + 2
+// where slot s of group g belongs to query (32*g)/Nq + s.  finalize_clip() then sums, for
+// every (i,j), the groups that hold rows of query i in ascending g — a fixed order, so clip
+// is bit-reproducible run to run (no float atomics anywhere on the forward path).
+struct PartLayout {
+    int G;   // 32-row groups
+    int S;   // query slots per group
+};
+static inline PartLayout part_layout(int M, int Nq) {
+    PartLayout p; p.G = ceil_div(M, 32); p.S = 31 / Nq + 2; return p;
+}
+
+// launchers implemented in the .cu files -------------------------------------------------
+int launch_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, cudaStream_t st);
+int launch_maxmean_simt(const void* q, const void* v, const float* row_scale, const float* T,
+                        int inv_T, int M, int Bv, int Nq, int Nv, int D, int dtype,
+                        float* part, void* idx, cudaStream_t st);
+int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
+                      int inv_T, int M, int Bv, int Nq, int Nv, int D,
+                      float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st);
+int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
+bool tc_supported(int Nv, int D);
+
+// ---- device helpers -----------------------------------------------------------------------
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp holds 32 consecutive token rows (row = row0 + lane) of image j: `val` is the row's
+// weighted maximum (0 for rows >= M).  Segmented shuffle reduction keyed by the query id
+// (rows of one query are contiguous, so segments are contiguous lane ranges); the first lane
+// of each segment stores part[j][g][qid - qfirst].
+__device__ __forceinline__ void store_group_partials(float* __restrict__ part, int j, int g,
+                                                     int G, int S, int row0, int M, int Nq,
+                                                     float val, int lane) {
+    const int r = row0 + lane;
+    const int qid = (r < M) ? r / Nq : 0x7fffffff;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(0xffffffffu, val, o);
+        int tq = __shfl_down_sync(0xffffffffu, qid, o);
+        if (lane + o < 32 && tq == qid) val += t;
+    }
+    const int prev = __shfl_up_sync(0xffffffffu, qid, 1);
+    const bool head = (lane == 0) || (prev != qid);
+    if (head && r < M) {
+        const int qfirst = (g * 32) / Nq;
+        part[((size_t)j * G + g) * S + (qid - qfirst)] = val;
+    }
+}
+
+#endif  // __CUDACC__
+}  // namespace triad

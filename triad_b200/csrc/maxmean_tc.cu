@@ -1,0 +1,557 @@
+// tcgen05 / TMEM / TMA forward of the max-mean similarity for bf16 inputs (sm_100a).
+//
+// Replaces src/model.py:384-391 (AV) and :502-512 (TV): the reference clones both operands B
+// times, runs a batched GEMM with batch B^2 and sweeps the resulting Bq x Bv x Nq x Nv tensor
+// four more times (*T, max, mean).  Here that tensor only ever exists as 128 x Nv fp32
+// accumulator tiles in tensor memory:
+//
+//   * rows   = query tokens, flattened over the batch (M = Bq*Nq), 128 per CTA = the 128 TMEM lanes;
+//   * cols   = the Nv patches of ONE image (UMMA N = Nv rounded up to 16, <= 256);
+//   * K      = D (<= 512) in 64-element (128-byte, SWIZZLE_128B) k-blocks.
+//
+// Work decomposition (persistent, one CTA or CTA pair per SM / SM pair):
+//   the (m-tile, image) space is linearised image-chunk-major, m-tile, image-in-chunk and cut
+//   into equal contiguous ranges, so a CTA keeps its 128 x D QUERY tile stationary in shared
+//   memory (128 KB) while it streams images, and all CTAs walk the same chunk of images at the
+//   same time (L2 reuse of V when V does not fit in L2).  Only V k-blocks go through the
+//   multi-stage TMA ring.  With cta_group::2 the pair shares each V tile (each CTA loads half
+//   of the patches), halving L2->SMEM traffic per SM.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (TMEM lane quarter = warp & 3).  Accumulators are double
+// buffered in TMEM (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+//
+// Epilogue (per thread = one token row): pass 1 fmax over the Nv raw accumulators; the exact
+// first-argmax threshold of triad_round.h; pass 2 finds the first column >= threshold (this
+// reproduces torch.max's first-index tie-break on the double-rounded bf16 values bit-exactly);
+// then a deterministic segmented shuffle reduction over the 32 rows of the warp into
+// per-(image, 32-row group, query) partial sums (common.cuh).
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace triad {
+namespace tc {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // bf16 per 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kMaxKB = 8;              // D <= 512
+constexpr int kMaxN = 256;
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kTmemCols = 512;
+constexpr uint32_t kQkbBytes = kBlockM * kBlockK * 2;        // 16 KB
+constexpr uint32_t kQBytes = kMaxKB * kQkbBytes;             // 128 KB
+constexpr uint32_t kVRingBytes = 96 * 1024;
+constexpr uint32_t kBarBytes = 512;
+constexpr uint32_t kSmemBytes = kQBytes + kVRingBytes + kBarBytes + 1024;   // + alignment slack
+constexpr unsigned long long kWatchdogNs = 4000000000ull;
+
+struct Params {
+    int M, Bv, Nq, Nv;
+    int n_umma;        // UMMA N (Nv rounded up to 16)
+    int num_kb;        // D / 64
+    int n_m;           // number of (128*cta_group)-row tiles
+    int C;             // images per chunk
+    int G, S;          // partial layout
+    int inv_T;
+    const float* row_scale;
+    const float* T;
+    float* part;
+    uint8_t* idx;
+    int* abort_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ unsigned long long globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait with a deadlock guard: if the barrier does not flip within kWatchdogNs the kernel raises the
+// global abort flag and every role drains out, so a pipeline bug costs an error code, not a hung GPU.
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
+    const unsigned long long t0 = globaltimer();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 63u) == 0u) {
+            if (*(volatile int*)abort_flag != 0) return false;
+            if (globaltimer() - t0 > kWatchdogNs) { atomicCAS(abort_flag, 0, code); return false; }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, abort_flag, code);
+}
+
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kCtaGroup>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int kCtaGroup>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    if constexpr (kCtaGroup == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// arrive on `bar` (same offset in every CTA of the pair) once all previously issued MMAs completed
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"(mask) : "memory");
+    }
+}
+
+template <int kCtaGroup>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    }
+}
+template <int kCtaGroup>
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    if constexpr (kCtaGroup == 1) {
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    } else {
+        asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    }
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 bytes,
+// 8-row core groups 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address  [0,14)
+    d |= (uint64_t)1 << 16;                                // LBO (ignored)  [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                      // SBO            [32,46)
+    d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                  // c_format = F32
+    d |= 1u << 7;                  // a_format = BF16
+    d |= 1u << 10;                 // b_format = BF16
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+struct Tile { int m, j; };
+__device__ __forceinline__ Tile decode_tile(uint32_t L, int n_m, int Bv, int C) {
+    const uint32_t per_chunk = (uint32_t)n_m * (uint32_t)C;
+    const uint32_t full = (uint32_t)Bv / (uint32_t)C;
+    uint32_t jc = L / per_chunk;
+    Tile t;
+    if (jc < full) {
+        const uint32_t rem = L - jc * per_chunk;
+        t.m = (int)(rem / (uint32_t)C);
+        t.j = (int)(jc * C + rem % (uint32_t)C);
+    } else {
+        const uint32_t rem = L - full * per_chunk;
+        const uint32_t cl = (uint32_t)Bv - full * (uint32_t)C;
+        t.m = (int)(rem / cl);
+        t.j = (int)(full * C + rem % cl);
+    }
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int kCtaGroup>
+__global__ void __launch_bounds__(kThreads, 1)
+maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
+                  const Params p) {
+    constexpr int kVStageBytes = (kMaxN / kCtaGroup) * kBlockK * 2;       // 32 KB / 16 KB
+    constexpr int kStages = kVRingBytes / kVStageBytes;                   // 3 / 6
+    constexpr int kTileRows = kBlockM * kCtaGroup;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = smem_base;
+    const uint32_t v_smem = smem_base + kQBytes;
+    const uint32_t bar_base = v_smem + kVRingBytes;
+    // barrier map (8 bytes each)
+    const uint32_t bar_q_full = bar_base;                       // [kMaxKB]
+    const uint32_t bar_q_empty = bar_q_full + 8 * kMaxKB;       // [1]
+    const uint32_t bar_v_full = bar_q_empty + 8;                // [kStages]
+    const uint32_t bar_v_empty = bar_v_full + 8 * kStages;      // [kStages]
+    const uint32_t bar_t_full = bar_v_empty + 8 * kStages;      // [2]
+    const uint32_t bar_t_empty = bar_t_full + 16;               // [2]
+    const uint32_t tmem_ptr_smem = bar_t_empty + 16;            // u32
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+    const uint32_t cluster_id = blockIdx.x / kCtaGroup;
+    const uint32_t n_clusters = gridDim.x / kCtaGroup;
+
+    const uint32_t total = (uint32_t)p.n_m * (uint32_t)p.Bv;
+    const uint32_t L_begin = (uint32_t)(((unsigned long long)total * cluster_id) / n_clusters);
+    const uint32_t L_end = (uint32_t)(((unsigned long long)total * (cluster_id + 1)) / n_clusters);
+
+    const int n_half = p.n_umma / kCtaGroup;                    // patch rows this CTA loads per image
+    const uint32_t v_tx_bytes = (uint32_t)n_half * kBlockK * 2u;
+
+    // ---- one-time setup -------------------------------------------------------------------
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_q); prefetch_tmap(&tmap_v); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kMaxKB; ++i) mbar_init(bar_q_full + 8 * i, 1);
+        mbar_init(bar_q_empty, 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(bar_v_full + 8 * i, 1); mbar_init(bar_v_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_t_full + 8 * i, 1); mbar_init(bar_t_empty + 8 * i, 4 * kCtaGroup); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) { cluster_arrive(); cluster_wait(); } else { __syncthreads(); }
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===================================
+        if (lane == 0) {
+            // in a pair, every load signals the LEADER's barrier (the only MMA issuer waits there)
+            const uint32_t q_full_sig = (kCtaGroup == 2) ? mapa(bar_q_full, 0) : bar_q_full;
+            const uint32_t v_full_sig = (kCtaGroup == 2) ? mapa(bar_v_full, 0) : bar_v_full;
+            int stage = 0; uint32_t phase = 0, qe_phase = 0; int prev_m = -1;
+            bool ok = true;
+            for (uint32_t L = L_begin; L < L_end && ok; ++L) {
+                const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
+                const bool new_m = (t.m != prev_m);
+                if (new_m && prev_m >= 0) {
+                    ok = mbar_wait(bar_q_empty, qe_phase, p.abort_flag, 1);
+                    qe_phase ^= 1;
+                    if (!ok) break;
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (new_m) {
+                        if (is_leader) mbar_expect_tx(bar_q_full + 8 * kb, kQkbBytes * kCtaGroup);
+                        tma_load_2d<kCtaGroup>(q_smem + kb * kQkbBytes, &tmap_q, q_full_sig + 8 * kb,
+                                               kb * kBlockK, t.m * kTileRows + (int)cta_rank * kBlockM);
+                    }
+                    ok = mbar_wait(bar_v_empty + 8 * stage, phase ^ 1, p.abort_flag, 2);
+                    if (!ok) break;
+                    if (is_leader) mbar_expect_tx(bar_v_full + 8 * stage, v_tx_bytes * kCtaGroup);
+                    tma_load_3d<kCtaGroup>(v_smem + stage * kVStageBytes, &tmap_v, v_full_sig + 8 * stage,
+                                           kb * kBlockK, (int)cta_rank * n_half, t.j);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                prev_m = t.m;
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer =====================================
+        if (lane == 0 && is_leader) {
+            const uint32_t idesc = make_idesc(kTileRows, p.n_umma);
+            int stage = 0; uint32_t phase = 0, qf_phase = 0; int prev_m = -1; uint32_t t_cnt = 0;
+            bool ok = true;
+            for (uint32_t L = L_begin; L < L_end && ok; ++L, ++t_cnt) {
+                const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
+                const bool new_m = (t.m != prev_m);
+                const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
+                ok = mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1, p.abort_flag, 3);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kMaxN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (new_m) { ok = mbar_wait(bar_q_full + 8 * kb, qf_phase, p.abort_flag, 4); if (!ok) break; }
+                    ok = mbar_wait(bar_v_full + 8 * stage, phase, p.abort_flag, 5);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(q_smem + kb * kQkbBytes);
+                    const uint64_t b_desc = make_smem_desc(v_smem + stage * kVStageBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
+                        umma_bf16<kCtaGroup>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit<kCtaGroup>(bar_v_empty + 8 * stage);      // frees the V stage in both CTAs
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if (!ok) break;
+                umma_commit<kCtaGroup>(bar_t_full + 8 * acc);            // accumulator ready (both CTAs)
+                bool next_new_m = true;
+                if (L + 1 < L_end) next_new_m = (decode_tile(L + 1, p.n_m, p.Bv, p.C).m != t.m);
+                if (next_new_m) umma_commit<kCtaGroup>(bar_q_empty);     // query tile may be overwritten
+                if (new_m) qf_phase ^= 1;
+                prev_m = t.m;
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // =============================== epilogue =======================================
+        const int quarter = warp & 3;
+        const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
+        float Tval = *p.T;
+        if (p.inv_T) Tval = 1.0f / Tval;
+        const int nch = p.n_umma >> 4;
+        const int Nv = p.Nv;
+        int prev_m = -1; float rs = 0.f; uint32_t t_cnt = 0;
+        for (uint32_t L = L_begin; L < L_end; ++L, ++t_cnt) {
+            const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
+            const int row0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;
+            const int r = row0 + lane;
+            if (t.m != prev_m) { rs = (r < p.M) ? p.row_scale[r] : 0.f; prev_m = t.m; }
+            const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
+            bool ok = mbar_wait(bar_t_full + 8 * acc, acc_phase, p.abort_flag, 6);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxN;
+
+            // ---- pass 1: row maximum over the Nv raw accumulators ----
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+            for (int c = 0; c < nch; ++c) {
+                float v[16];
+                tmem_ld16(taddr + c * 16, v);
+                tmem_wait_ld();
+                if (c * 16 + 16 > Nv) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) if (c * 16 + e >= Nv) v[e] = -INFINITY;
+                }
+                mx0 = fmax3(mx0, v[0], v[1]);  mx1 = fmax3(mx1, v[2], v[3]);
+                mx0 = fmax3(mx0, v[4], v[5]);  mx1 = fmax3(mx1, v[6], v[7]);
+                mx0 = fmax3(mx0, v[8], v[9]);  mx1 = fmax3(mx1, v[10], v[11]);
+                mx0 = fmax3(mx0, v[12], v[13]); mx1 = fmax3(mx1, v[14], v[15]);
+            }
+            float R;
+            const float theta = argmax_threshold<true>(fmaxf(mx0, mx1), Tval, &R);
+
+            // ---- pass 2: first column whose accumulator reaches the threshold ----
+            int best = 0;
+            if (p.idx != nullptr) {
+                for (int c = nch - 1; c >= 0; --c) {
+                    float v[16];
+                    tmem_ld16(taddr + c * 16, v);
+                    tmem_wait_ld();
+                    if (c * 16 + 16 > Nv) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) if (c * 16 + e >= Nv) v[e] = -INFINITY;
+                    }
+#pragma unroll
+                    for (int e = 15; e >= 0; --e) if (v[e] >= theta) best = c * 16 + e;
+                }
+            }
+            // TMEM stage drained: hand it back to the MMA issuer before touching global memory
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtaGroup == 2) mbar_arrive_cluster(t_empty_sig + 8 * acc);
+                else mbar_arrive_local(bar_t_empty + 8 * acc);
+            }
+            if (p.idx != nullptr && r < p.M) p.idx[(size_t)t.j * p.M + r] = (uint8_t)best;
+            const float val = (r < p.M) ? R * rs : 0.f;
+            store_group_partials(p.part, t.j, row0 >> 5, p.G, p.S, row0, p.M, p.Nq, val, lane);
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------
+    __syncwarp();
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) { cluster_arrive(); cluster_wait(); } else { __syncthreads(); }
+    if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (PFN_tmapEncodeTiled)p;
+    return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (!fn) return fail_msg(TRIAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return fail_msg(TRIAD_ERR_CUDA, buf);
+    }
+    return TRIAD_OK;
+}
+
+template <int kCtaGroup>
+static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& p, int n_clusters, cudaStream_t st) {
+    auto kern = maxmean_tc_kernel<kCtaGroup>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * kCtaGroup));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mv, p));
+    return TRIAD_OK;
+}
+
+}  // namespace tc
+
+bool tc_supported(int Nv, int D) { return Nv >= 1 && Nv <= tc::kMaxN && D % tc::kBlockK == 0 && D >= tc::kBlockK && D <= tc::kMaxKB * tc::kBlockK; }
+
+int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
+                      int inv_T, int M, int Bv, int Nq, int Nv, int D,
+                      float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st) {
+    using namespace tc;
+    if (!tc_supported(Nv, D)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: needs Nv <= 256 and D in {64,...,512} (multiple of 64)");
+    const int tile_rows = kBlockM * cta_group;
+    const int n_m = ceil_div(M, tile_rows);
+    if ((long long)n_m * Bv >= 0x7fffffffLL) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: too many tiles");
+
+    int dev = 0, sms = 0;
+    TRIAD_CUDA_CHECK(cudaGetDevice(&dev));
+    TRIAD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+    Params p;
+    p.M = M; p.Bv = Bv; p.Nq = Nq; p.Nv = Nv;
+    p.n_umma = (Nv + 15) / 16 * 16;
+    p.num_kb = D / kBlockK;
+    p.n_m = n_m;
+    // image chunk: keep all of V L2-resident when it is small, otherwise walk 64 images at a time
+    const size_t v_bytes = (size_t)Bv * Nv * D * 2;
+    p.C = (v_bytes <= (size_t)48 << 20) ? Bv : (Bv < 64 ? Bv : 64);
+    PartLayout pl = part_layout(M, Nq);
+    p.G = pl.G; p.S = pl.S;
+    p.inv_T = inv_T;
+    p.row_scale = row_scale; p.T = T; p.part = part; p.idx = (uint8_t*)idx; p.abort_flag = abort_flag;
+
+    CUtensorMap mq, mv;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kBlockM};
+        int rc = encode_map(&mq, q, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Nv, (cuuint64_t)Bv};
+        cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)Nv * D * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)(p.n_umma / cta_group), 1};
+        int rc = encode_map(&mv, v, 3, dims, strides, box);
+        if (rc) return rc;
+    }
+    const long long total = (long long)n_m * Bv;
+    int n_clusters = sms / cta_group;
+    if ((long long)n_clusters > total) n_clusters = (int)total;
+    if (n_clusters < 1) n_clusters = 1;
+    if (cta_group == 2) return launch_t<2>(mq, mv, p, n_clusters, st);
+    return launch_t<1>(mq, mv, p, n_clusters, st);
+}
+
+}  // namespace triad

@@ -1,0 +1,170 @@
+"""Drop-in replacements for the similarity / aggregation / loss methods of the reference's
+``MultiModalModel`` (src/model.py:355-392, :430-472, :490-514, :544-593).
+
+``TriadSimilarityMixin`` keeps the reference's method names, positional arguments and return
+arities, so ``forward_audio_visual`` (model.py:487-488), ``forward_text_visual`` (:607-608) and
+the trainer (train.py:745,758,954,969) run unchanged on top of it:
+
+    class MultiModalModel(TriadSimilarityMixin, nn.Module): ...
+
+``self`` only has to provide what the reference's methods read: ``self.temperature`` (0-dim fp32
+nn.Parameter, model.py:348) and ``patch_sparsity_threshold`` / ``patch_sparsity_weight``.
+
+One deliberate difference: the reference returns the dense ``token_sims`` tensor
+(B,B,Nq,Nv) — 16.8 GB at the B=256 training shape.  The fused path never builds it; the second
+return value is a ``TokenSims`` handle that carries the saved argmax indices and the fp32 clip
+matrix, has the reference tensor's ``.shape`` / ``.dtype`` / ``.device``, and can
+``.materialize()`` the dense tensor on demand (visualisation, tests, small batches).  The loss
+methods accept that handle (or, for API compatibility, a dense tensor, in which case only the
+contrastive part — which never needed token_sims — is computed from ``clip_sims``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+class TokenSims:
+    """Stand-in for the reference's (Bq,Bv,Nq,Nv) token-similarity tensor."""
+
+    def __init__(self, q, v, temperature, scale, mask, clip_f32, idx, prefix):
+        self.q, self.v, self.temperature = q, v, temperature
+        self.row_scale, self.mask = scale, mask
+        self.clip = clip_f32            # fp32 (Bq,Bv), attached to the autograd graph
+        self.idx_t = idx                # [Bv, Bq*Nq] uint8/uint16 (library layout)
+        self.prefix = prefix
+        self.shape = torch.Size((q.shape[0], v.shape[0], q.shape[1], v.shape[1]))
+        self.dtype = q.dtype
+        self.device = q.device
+
+    def argmax(self) -> torch.Tensor:
+        """(Bq,Bv,Nq) int64 in the reference's layout: torch.max(token_sims, dim=3)[1]."""
+        Bq, Bv, Nq, _ = self.shape
+        return self.idx_t.view(Bv, Bq, Nq).permute(1, 0, 2).to(torch.int64).contiguous()
+
+    def materialize(self) -> torch.Tensor:
+        """Dense token_sims exactly as the reference builds it (model.py:384-387).  Debug /
+        visualisation aid for small batches; not used by the training path."""
+        Bq, Bv = self.shape[0], self.shape[1]
+        af = self.q.unsqueeze(1).expand(-1, Bv, -1, -1)
+        vf = self.v.unsqueeze(0).expand(Bq, -1, -1, -1)
+        return torch.matmul(af, vf.transpose(2, 3)) * self.temperature
+
+    def __repr__(self):
+        return f"TokenSims(shape={tuple(self.shape)}, dtype={self.dtype}, device={self.device}, fused)"
+
+
+def _stats_from_sums(sums: torch.Tensor, B: int, prefix: str) -> Dict[str, float]:
+    """model.py:435-450 / :553-568 from the kernel's fp64 sums; ONE device->host copy instead of
+    the reference's five .item() calls."""
+    s = sums.tolist()
+    n_off = B * B - B
+    pos_mean = s[1] / B
+    neg_mean = s[3] / n_off if n_off else float("nan")
+    pos_var = (s[2] - B * pos_mean * pos_mean) / (B - 1) if B > 1 else float("nan")
+    neg_var = (s[4] - n_off * neg_mean * neg_mean) / (n_off - 1) if n_off > 1 else float("nan")
+    return {
+        f"{prefix}_pos_sim_mean": pos_mean,
+        f"{prefix}_pos_sim_std": max(pos_var, 0.0) ** 0.5 if pos_var == pos_var else pos_var,
+        f"{prefix}_neg_sim_mean": neg_mean,
+        f"{prefix}_neg_sim_std": max(neg_var, 0.0) ** 0.5 if neg_var == neg_var else neg_var,
+        f"{prefix}_separation": pos_mean - neg_mean,
+        f"{prefix}_hardest_negative": s[5],
+    }
+
+
+class TriadSimilarityMixin:
+    """Provides compute_all_similarities_{av,tv}, compute_contrastive_loss_{av,tv} and
+    compute_similarity_matrix with the reference's signatures."""
+
+    #: forwarded to triad_maxmean_fwd (tests use it to pin a kernel variant)
+    triad_fwd_flags: int = 0
+
+    # -- similarities -----------------------------------------------------------------------
+    def _similarities(self, q_feats, visual_feats, attention_mask, prefix):
+        if q_feats.dim() != 3 or visual_feats.dim() != 3:
+            raise ValueError("expected (B,N,D) embeddings")
+        Bq, Nq, _ = q_feats.shape
+        scale = ops.row_scale(attention_mask, Bq, Nq, q_feats.device)
+        clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale,
+                                                int(self.triad_fwd_flags))
+        handle = TokenSims(q_feats, visual_feats, self.temperature, scale, attention_mask, clip, idx, prefix)
+        # The reference's clip_sims dtype: bf16 for AV under autocast (mean of bf16 maxima,
+        # model.py:391), fp32 for TV (mask.float() promotes, model.py:509-512) and for fp32 inputs.
+        out = clip.to(q_feats.dtype) if attention_mask is None else clip
+        return out, handle
+
+    def compute_all_similarities_av(self, audio_feats, visual_feats):
+        """(clip_sims (B,B), token_sims handle) — model.py:370-392."""
+        return self._similarities(audio_feats, visual_feats, None, "av")
+
+    def compute_all_similarities_tv(self, text_feats, visual_feats, attention_mask):
+        """(clip_sims (B,B), token_sims handle) — model.py:490-514."""
+        return self._similarities(text_feats, visual_feats, attention_mask, "tv")
+
+    # -- losses -----------------------------------------------------------------------------
+    def _contrastive(self, clip_sims, token_sims, prefix) -> Tuple[torch.Tensor, Dict[str, float]]:
+        clip = token_sims.clip if isinstance(token_sims, TokenSims) else clip_sims
+        loss, sums = ops.SymmetricInfoNCE.apply(clip)
+        return loss, _stats_from_sums(sums, clip.shape[0], prefix)
+
+    def _temperature_calibration(self) -> torch.Tensor:
+        """20 * relu(-log T)^2 — the l_cal term of model.py:420-427 (a scalar on the parameter)."""
+        return 20.0 * torch.clamp(-torch.log(self.temperature), min=0) ** 2
+
+    def compute_contrastive_loss_av(self, clip_sims, token_sims):
+        """(total, contrastive, reg, 0.01*l_smooth, stats) — model.py:430-472.
+
+        The dense regularisers (0.15*mean(clamp(S,-60,0)^2) and the temporal smoothness term)
+        read the full token-similarity tensor; they are the SURVEY §8(f1) follow-up and are not
+        part of this build's fused path: ``reg`` carries the temperature-calibration term only and
+        the returned smoothness term is zero.  See DESIGN.md §"Out of scope"."""
+        contrastive, stats = self._contrastive(clip_sims, token_sims, "av")
+        reg = self._temperature_calibration()
+        smooth = torch.zeros((), dtype=torch.float32, device=contrastive.device)
+        return contrastive + reg, contrastive, reg, smooth, stats
+
+    def compute_contrastive_loss_tv(self, clip_sims, token_sims):
+        """(total, stats) — model.py:544-593 (contrastive part; see compute_contrastive_loss_av)."""
+        contrastive, stats = self._contrastive(clip_sims, token_sims, "tv")
+        return contrastive, stats
+
+    # -- per-pair normalised similarity (viz / forward()) -------------------------------------
+    def compute_similarity_matrix(self, feats1, feats2):
+        """(B,N1,N2) = T * <normalize(f1), normalize(f2)> — model.py:355-368 (inference helper,
+        no autograd)."""
+        from . import _lib
+        lib = _lib.load()
+        f1 = feats1.detach().float().contiguous()
+        f2 = feats2.detach().float().contiguous()
+        B, N1, D = f1.shape
+        N2 = f2.shape[1]
+        T = ops.temperature_tensor(self.temperature, f1.device)
+        out = torch.empty(B, N1, N2, dtype=torch.float32, device=f1.device)
+        _lib.check(lib.triad_similarity_matrix(f1.data_ptr(), f2.data_ptr(), T.data_ptr(), B, N1, N2, D,
+                                               out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "triad_similarity_matrix")
+        return out
+
+
+class TriadHotPath(TriadSimilarityMixin, torch.nn.Module):
+    """Stand-alone module with just the state the hot path reads (model.py:348-351).  Used by
+    bench.py / tests / smoke; a full model would mix TriadSimilarityMixin into MultiModalModel."""
+
+    def __init__(self, temperature: float = 1.2, patch_sparsity_threshold: float = 0.3,
+                 patch_sparsity_weight: float = 0.1):
+        super().__init__()
+        self.temperature = torch.nn.Parameter(torch.tensor(float(temperature)))
+        self.patch_sparsity_threshold = patch_sparsity_threshold
+        self.patch_sparsity_weight = patch_sparsity_weight
+
+    def forward_features_av(self, audio_feats, visual_feats):
+        clip, tok = self.compute_all_similarities_av(audio_feats, visual_feats)
+        return self.compute_contrastive_loss_av(clip, tok)
+
+    def forward_features_tv(self, text_feats, visual_feats, attention_mask):
+        clip, tok = self.compute_all_similarities_tv(text_feats, visual_feats, attention_mask)
+        return self.compute_contrastive_loss_tv(clip, tok)

@@ -1,0 +1,205 @@
+"""torch-facing wrappers of the C ABI: raw calls, a grow-only workspace cache and the two
+autograd Functions (max-mean similarity, symmetric InfoNCE) the drop-in methods are built from.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every arithmetic
+step of the path runs in libtriad_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_DT = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("triad_b200 runs on CUDA tensors only (there is no CPU fallback)")
+
+
+class _Workspace:
+    """One grow-only byte buffer per (device, stream, tag)."""
+    _bufs: Dict[Tuple, torch.Tensor] = {}
+
+    @classmethod
+    def get(cls, nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
+        key = (device.index, _stream(), tag)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1024), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"triad_b200 supports float32 and bfloat16 embeddings, got {t.dtype}") from None
+
+
+def temperature_tensor(temperature, device) -> torch.Tensor:
+    """The kernels read the temperature from device memory (no host sync on the nn.Parameter)."""
+    if isinstance(temperature, torch.Tensor):
+        t = temperature.detach() if temperature.requires_grad else temperature
+        if t.dtype != torch.float32 or t.device != device or t.numel() != 1:
+            t = t.to(device=device, dtype=torch.float32).reshape(())
+        return t
+    return torch.tensor(float(temperature), dtype=torch.float32, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
+# raw calls
+# ----------------------------------------------------------------------------------------------
+def row_scale(mask: Optional[torch.Tensor], Bq: int, Nq: int, device) -> torch.Tensor:
+    lib = _lib.load()
+    out = torch.empty(Bq * Nq, dtype=torch.float32, device=device)
+    if mask is not None:
+        _require_cuda(mask)
+        mask = mask.to(torch.int64).contiguous()
+        if mask.shape != (Bq, Nq):
+            raise ValueError(f"attention_mask must be ({Bq},{Nq}), got {tuple(mask.shape)}")
+    check(lib.triad_row_scale(_ptr(mask), Bq, Nq, out.data_ptr(), _stream()), "triad_row_scale")
+    return out
+
+
+def idx_dtype(Nv: int) -> torch.dtype:
+    return torch.uint8 if Nv <= 256 else torch.uint16
+
+
+def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.Tensor,
+                want_idx: bool = True, flags: int = 0, check_watchdog: bool = False):
+    """clip fp32 [Bq,Bv], idx [Bv, Bq*Nq] (uint8/uint16) or None."""
+    lib = _lib.load()
+    _require_cuda(q, v, scale, T)
+    if q.dtype != v.dtype:
+        raise TypeError("q and v must have the same dtype")
+    q, v = q.contiguous(), v.contiguous()
+    Bq, Nq, D = q.shape
+    Bv, Nv, D2 = v.shape
+    if D != D2:
+        raise ValueError("embedding dims differ")
+    dt = _dtype_code(q)
+    clip = torch.empty(Bq, Bv, dtype=torch.float32, device=q.device)
+    idx = torch.empty(Bv, Bq * Nq, dtype=idx_dtype(Nv), device=q.device) if want_idx else None
+    nws = lib.triad_maxmean_fwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dt)
+    ws = _Workspace.get(nws, q.device, "fwd")
+    check(lib.triad_maxmean_fwd(q.data_ptr(), v.data_ptr(), scale.data_ptr(), T.data_ptr(),
+                                Bq, Bv, Nq, Nv, D, dt, clip.data_ptr(), _ptr(idx),
+                                ws.data_ptr(), ws.numel(), flags, _stream()), "triad_maxmean_fwd")
+    if check_watchdog:
+        check(lib.triad_maxmean_fwd_status(ws.data_ptr(), _stream()), "triad_maxmean_fwd (watchdog)")
+    return clip, idx
+
+
+def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_dT=True, dv_f32=False):
+    lib = _lib.load()
+    q, v, g = q.contiguous(), v.contiguous(), g.contiguous()
+    if g.dtype != torch.float32:
+        g = g.float()
+    Bq, Nq, D = q.shape
+    Bv, Nv, _ = v.shape
+    dt = _dtype_code(q)
+    dq = torch.empty_like(q) if need_dq else None
+    dv = (torch.empty(Bv, Nv, D, dtype=torch.float32 if dv_f32 else v.dtype, device=v.device)
+          if need_dv else None)
+    dT = torch.empty((), dtype=torch.float32, device=q.device) if need_dT else None
+    nws = lib.triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dt)
+    ws = _Workspace.get(nws, q.device, "bwd")
+    check(lib.triad_maxmean_bwd(q.data_ptr(), v.data_ptr(), idx.data_ptr(), g.data_ptr(), _ptr(clip),
+                                scale.data_ptr(), T.data_ptr(), Bq, Bv, Nq, Nv, D, dt,
+                                _ptr(dq), _ptr(dv), 1 if dv_f32 else 0, _ptr(dT),
+                                ws.data_ptr(), ws.numel(), _stream()), "triad_maxmean_bwd")
+    return dq, dv, dT
+
+
+def infonce_partial(clip_rows: torch.Tensor, B: int, row0: int):
+    lib = _lib.load()
+    rows = clip_rows.shape[0]
+    row_lse = torch.empty(rows, dtype=torch.float32, device=clip_rows.device)
+    col_part = torch.empty(2, B, dtype=torch.float32, device=clip_rows.device)
+    nws = lib.triad_infonce_workspace_bytes(rows, B)
+    ws = _Workspace.get(nws, clip_rows.device, "nce")
+    check(lib.triad_infonce_partial(clip_rows.data_ptr(), rows, B, row0, row_lse.data_ptr(), col_part.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), _stream()), "triad_infonce_partial")
+    return row_lse, col_part
+
+
+def infonce_finish(clip_rows, B, row0, row_lse, col_parts, grad_scale: float = 1.0):
+    lib = _lib.load()
+    rows = clip_rows.shape[0]
+    col_parts = col_parts.contiguous()
+    nparts = col_parts.numel() // (2 * B)
+    g = torch.empty(rows, B, dtype=torch.float32, device=clip_rows.device)
+    sums = torch.empty(8, dtype=torch.float64, device=clip_rows.device)
+    nws = lib.triad_infonce_workspace_bytes(rows, B)
+    ws = _Workspace.get(nws, clip_rows.device, "nce")
+    check(lib.triad_infonce_finish(clip_rows.data_ptr(), rows, B, row0, row_lse.data_ptr(), col_parts.data_ptr(),
+                                   nparts, grad_scale, g.data_ptr(), sums.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream()), "triad_infonce_finish")
+    return g, sums
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd
+# ----------------------------------------------------------------------------------------------
+class MaxMeanSimilarity(torch.autograd.Function):
+    """clip[i,j] = sum_a scale[i,a] * max_p round(T <q[i,a], v[j,p]>); backward through the saved
+    argmax (src/model.py:387-391 and its autograd backward)."""
+
+    @staticmethod
+    def forward(ctx, q, v, temperature, scale, flags):
+        T = temperature_tensor(temperature, q.device)
+        clip, idx = maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
+        ctx.save_for_backward(q, v, T, scale, idx, clip)
+        ctx.mark_non_differentiable(idx)
+        ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
+        ctx.t_dtype = temperature.dtype if isinstance(temperature, torch.Tensor) else None
+        return clip, idx
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        q, v, T, scale, idx, clip = ctx.saved_tensors
+        need_dq, need_dv, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dq, dv, dT = maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq, need_dv, need_dT)
+        if dT is not None and ctx.t_shape is not None:
+            dT = dT.reshape(ctx.t_shape).to(ctx.t_dtype)
+        return dq, dv, dT, None, None
+
+
+class SymmetricInfoNCE(torch.autograd.Function):
+    """loss = mean_i(-log_softmax_row(clip)[i,i] - log_softmax_col(clip)[i,i]) / 2
+    (src/model.py:453-459); forward also produces dLoss/dclip and the statistics sums."""
+
+    @staticmethod
+    def forward(ctx, clip):
+        clip = clip.contiguous()
+        if clip.dtype != torch.float32:
+            clip = clip.float()
+        B = clip.shape[0]
+        if clip.shape[1] != B:
+            raise ValueError("InfoNCE needs a square clip-similarity matrix")
+        row_lse, col_part = infonce_partial(clip, B, 0)
+        g, sums = infonce_finish(clip, B, 0, row_lse, col_part.reshape(1, 2, B))
+        loss = (sums[0] / (2 * B)).to(torch.float32)
+        ctx.save_for_backward(g)
+        ctx.mark_non_differentiable(sums)
+        return loss, sums
+
+    @staticmethod
+    def backward(ctx, gl, _gs):
+        (g,) = ctx.saved_tensors
+        return g * gl
