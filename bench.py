@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the fused max-mean similarity + symmetric InfoNCE path (fwd + bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl triad|reference] [--config cfg2|cfg3|cfg4]
+
+metric: clip-pairs/sec = B_global^2 / t(step)   (BASELINE.json).  One "step" = one forward + backward of
+the hot path over one synthetic batch.  N=1 runs BASELINE cfg 2 (B=256, 250 frames x 256 patches, D=512,
+bf16); N>1 (launched by torchrun, one rank per GPU) runs cfg 4 (B=8192 global, rows sharded over the ranks,
+NCCL all-gather / reduce-scatter).  Rank 0 prints ONE JSON line.
+
+`value`  : device-resident inputs, CUDA-event timing, max over ranks.
+`e2e`    : the same step through the public drop-in API starting from PINNED HOST buffers (H2D copies of the
+           embeddings and the D2H read of the loss inside the timed region).
+`roofline`: the tcgen05 forward kernel against the measured bf16 peak (MEASURED_PEAKS.json).
+`cpu_baseline`: the oracle's port of the reference's own (materialising) step on this box's host cores.
+`--impl reference`: only that CPU port, as its own JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "cfg2": dict(B=256, Nq=250, Nv=256, D=512, masked=False,
+                 name="cfg2: B=256, 250 HuBERT frames x 256 DINOv2 patches, D=512, bf16 fwd+bwd"),
+    "cfg3": dict(B=512, Nq=77, Nv=256, D=512, masked=True,
+                 name="cfg3: B=512, 77 text tokens (ragged masks, n_i in [8,77]) x 256 patches, D=512, bf16 fwd+bwd"),
+    "cfg4": dict(B=8192, Nq=250, Nv=256, D=512, masked=False,
+                 name="cfg4: B=8192 global, 250 x 256, D=512, bf16 fwd+bwd, rows sharded over ranks"),
+}
+KERNELS_PER_STEP = 11    # row_scale, maxmean_tc, finalize_clip, nce_partial, nce_combine x2, nce_finish,
+                         # nce_final_reduce, dq_gather, dv_scatter, dT
+
+
+def algorithmic_flops(B_rows, B_cols, n_tokens_total, Nv, D):
+    """2*Bcols*(sum n_i)*Nv*D forward + 4*Bcols*(sum n_i)*D sparse backward."""
+    return 2.0 * B_cols * n_tokens_total * Nv * D, 4.0 * B_cols * n_tokens_total * D
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        hi = sorted(sm)[len(sm) // 2:]            # the samples under load are the upper half when the region is short
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_upper_half_median": statistics.median(hi)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's port of the reference step (materialises token_sims, autograd)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(cfg, B_sample):
+    import torch
+    from oracle import oracle as O
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    q, v, mask = O.make_inputs(B_sample, cfg["Nq"], cfg["Nv"], cfg["D"], torch.float32, seed=1234,
+                               masked=cfg["masked"], min_len=8)
+    T = torch.tensor(1.5, requires_grad=True)
+    q.requires_grad_(True)
+    v.requires_grad_(True)
+
+    def step():
+        q.grad = v.grad = T.grad = None
+        loss, _, _ = O.reference_step_autograd(q, v, T, mask)
+        return float(loss)
+    return step
+
+
+def cpu_baseline(cfg, budget_s=12.0, B_sample=32):
+    step = cpu_reference_step_factory(cfg, B_sample)
+    step()                                   # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        step(); n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 50:
+            break
+    import torch
+    return {"value": B_sample * B_sample * n / el, "unit": "clip-pairs/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"oracle.reference_step_autograd (the reference's materialising fwd+bwd, fp32) on a "
+                      f"B={B_sample} sub-batch of the same shape (Nq={cfg['Nq']}, Nv={cfg['Nv']}, D={cfg['D']}), "
+                      f"{n} steps in {el:.1f} s; pairs/s is per-pair work, so it transfers to the full batch"}
+
+
+def run_reference(args, cfg_key):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    Python and does not travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cfg = CONFIGS[cfg_key]
+    Bs = 32
+    step = cpu_reference_step_factory(cfg, Bs)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    val = Bs * Bs * args.steps / el
+    cores = torch.get_num_threads()
+    sample = (f"each step = fwd+bwd of the reference's materialising path (oracle port, fp32) on a B={Bs} sub-batch "
+              f"of {cfg['name']}")
+    print(json.dumps({
+        "impl": "reference", "metric": "clip-pairs/sec", "value": val, "unit": "clip-pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "sample_batch": Bs},
+        "cpu_baseline": {"value": val, "unit": "clip-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "clip-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def make_device_inputs(cfg, B_local, seed, device, n_sets):
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    sets = []
+    for _ in range(n_sets):
+        q = (torch.randn(B_local, cfg["Nq"], cfg["D"], generator=g, device=device) / cfg["D"] ** 0.5).to(torch.bfloat16)
+        v = (torch.randn(B_local, cfg["Nv"], cfg["D"], generator=g, device=device) / cfg["D"] ** 0.5).to(torch.bfloat16)
+        mask = None
+        if cfg["masked"]:
+            lens = torch.randint(8, cfg["Nq"] + 1, (B_local,), generator=g, device=device)
+            lens[0] = cfg["Nq"]
+            mask = (torch.arange(cfg["Nq"], device=device)[None, :] < lens[:, None]).to(torch.int64)
+        sets.append((q, v, mask))
+    return sets
+
+
+def run_triad(args, cfg_key):
+    import torch
+    import torch.distributed as dist
+    import triad_b200
+    from triad_b200 import _lib
+    from triad_b200.dist import sharded_contrastive_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.triad_device_check(local), "triad_device_check")
+
+    cfg = CONFIGS[cfg_key]
+    B = cfg["B"]
+    assert B % world == 0
+    Bl = B // world
+    n_sets = 3 if world == 1 else 2
+    sets = make_device_inputs(cfg, Bl, 1234 + rank, dev, n_sets)
+    in_bytes = sum(t.numel() * t.element_size() for t in sets[0][:2])
+    model = triad_b200.TriadHotPath(temperature=1.5).to(dev)
+    T = model.temperature
+    tokens_local = int(sets[0][2].sum().item()) if cfg["masked"] else Bl * cfg["Nq"]
+    fwd_ev = []
+
+    def step_single(q, v, mask, record=False):
+        q.grad = v.grad = T.grad = None
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if mask is None:
+            clip, tok = model.compute_all_similarities_av(q, v)
+        else:
+            clip, tok = model.compute_all_similarities_tv(q, v, mask)
+        if record:
+            e1.record(); fwd_ev.append((e0, e1))
+        if mask is None:
+            total, con, reg, smooth, stats = model.compute_contrastive_loss_av(clip, tok)
+        else:
+            total, stats = model.compute_contrastive_loss_tv(clip, tok)
+        total.backward()
+        return total
+
+    def step_sharded(q, v, mask, record=False):
+        out = sharded_contrastive_step(q, v, T, mask)
+        return out["loss"]
+
+    step = step_single if world == 1 else step_sharded
+    for s in sets:
+        s[0].requires_grad_(world == 1); s[1].requires_grad_(world == 1)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, K):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(*sets[i % n_sets])
+    with ClockSampler(local) as clocks:
+        ms = timed(lambda i: step(*sets[i % n_sets], record=True), args.steps)
+    value = float(B) * B / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host inputs -> H2D -> step -> loss D2H --------------------------
+    host = [(q.detach().cpu().pin_memory(), v.detach().cpu().pin_memory(),
+             None if m is None else m.cpu().pin_memory()) for (q, v, m) in sets]
+    d2h = {"bytes": 0}
+
+    def e2e_step(i):
+        hq, hv, hm = host[i % n_sets]
+        q = hq.to(dev, non_blocking=True).requires_grad_(world == 1)
+        v = hv.to(dev, non_blocking=True).requires_grad_(world == 1)
+        m = None if hm is None else hm.to(dev, non_blocking=True)
+        loss = step(q, v, m)
+        d2h["bytes"] = 4
+        return loss.item()                    # D2H read of the step's result
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    e2e_ms = timed(e2e_step, args.steps)
+    h2d = in_bytes + (host[0][2].numel() * 8 if host[0][2] is not None else 0)
+
+    # ---- roofline of the dominant kernel (tcgen05 forward) ---------------------------------------
+    peak, peak_sustained, peak_src = measured_peaks()
+    roof = None
+    if fwd_ev:
+        fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+        f_fwd, f_bwd = algorithmic_flops(Bl, B, tokens_local, cfg["Nv"], cfg["D"])
+        achieved = f_fwd / (fwd_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(cfg_key)
+        roof = {"bound": "tensor", "kernel": "maxmean_tc_kernel (fwd call: memset + kernel + finalize_clip)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": f"{peak_src} (burst); sustained {peak_sustained}",
+                "frac_of_sustained": achieved / peak_sustained, "ms": fwd_ms, "traffic": traffic,
+                "step_flops": f_fwd + f_bwd,
+                "step_frac_of_peak": (f_fwd + f_bwd) * world / (ms * 1e-3) / 1e12 / (peak * world)}
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "clip-pairs/sec", "value": value, "unit": "clip-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg["name"], "global_batch": B, "rows_per_rank": Bl,
+                       "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": f"{n_sets} rotating input sets ({n_sets * in_bytes / 2**20:.0f} MiB) > 126 MB L2, "
+                             "so every step reads its embeddings from HBM"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": float(B) * B / (e2e_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h["bytes"]},
+            "gpu_launches": (KERNELS_PER_STEP if world == 1 else KERNELS_PER_STEP - 1) * args.steps,
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="triad", choices=["triad", "reference"])
+    ap.add_argument("--config", default="auto", choices=["auto"] + list(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world > 1:
+        args.gpus = world
+    cfg_key = args.config if args.config != "auto" else ("cfg2" if max(args.gpus, world) == 1 else "cfg4")
+    if args.impl == "reference":
+        run_reference(args, cfg_key)
+    else:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 "
+                             "--nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+        run_triad(args, cfg_key)
+
+
+if __name__ == "__main__":
+    main()

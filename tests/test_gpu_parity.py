@@ -1,0 +1,278 @@
+"""GPU tier: the CUDA path, called through the drop-in methods (-> ctypes -> C ABI), against
+(1) the golden vectors of the unmodified reference and (2) the CPU oracle, plus size-independent
+properties at the full BASELINE cfg-2 shape.
+
+Tolerances are the north star's: argmax indices bit-exact; loss / similarity / gradients within
+1e-4 relative for fp32 inputs and 1e-2 for bf16 inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from oracle.cases import CASES, build_inputs, projection
+from tests.helpers import check_inputs_reproduce, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_SIMT, FWD_1CTA = 1, 2
+
+
+def _model(T, flags=0):
+    import triad_b200
+    m = triad_b200.TriadHotPath(temperature=T).cuda()
+    m.triad_fwd_flags = flags
+    return m
+
+
+def _run_case(case, flags):
+    q, v, mask, T = build_inputs(case)
+    m = _model(T, flags)
+    qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    if case.kind == "av":
+        clip, tok = m.compute_all_similarities_av(qd, vd)
+        total, con, reg, smooth, stats = m.compute_contrastive_loss_av(clip, tok)
+    else:
+        clip, tok = m.compute_all_similarities_tv(qd, vd, mask.cuda())
+        con, stats = m.compute_contrastive_loss_tv(clip, tok)
+    con.backward()
+    torch.cuda.synchronize()
+    return q, v, mask, T, m, qd, vd, clip, tok, con, stats
+
+
+def _variants(case):
+    if case.dtype == "fp32":
+        return [0]
+    return [0, FWD_1CTA, FWD_SIMT]        # tcgen05 cta_group::2, cta_group::1, CUDA-core
+
+
+ALL = [(c, f) for c in CASES for f in _variants(c)]
+
+
+@pytest.mark.parametrize("case,flags", ALL, ids=[f"{c.name}-f{f}" for c, f in ALL])
+def test_golden_parity(case, flags):
+    gold = load_golden(case.name)
+    q, v, mask, T, m, qd, vd, clip, tok, con, stats = _run_case(case, flags)
+    check_inputs_reproduce(gold, q, v)
+    fp32 = case.dtype == "fp32"
+    tol = 1e-4 if fp32 else 1e-2
+
+    # (1) argmax patch indices: bit-exact against the reference's torch.max
+    assert tok.shape == (case.B, case.B, case.Nq, case.Nv)
+    assert np.array_equal(tok.argmax().cpu().numpy(), gold["idx"].astype(np.int64))
+
+    # (2) clip similarity: same dtype as the reference returns, values within tolerance
+    assert clip.dtype == (torch.bfloat16 if bool(gold["clip_is_bf16"]) else torch.float32)
+    assert rel_err(clip.float().cpu(), gold["clip"]) < tol
+    oracle = O.contrastive_step_closed_form(q, v, T, mask)
+    ctol = 2e-6 if fp32 else 1e-5         # fp32 clip vs oracle fp32 clip (a flipped bf16 rounding moves one row max by 1 ulp)
+    assert rel_err(tok.clip.detach().cpu(), oracle["clip"]) < ctol
+
+    # (3) loss and gradients vs the reference
+    assert abs(con.item() - float(gold["contrastive"])) <= tol * abs(float(gold["contrastive"]))
+    P = projection(case)
+    dq = qd.grad.double().cpu() @ P if P is not None else qd.grad.double().cpu()
+    dv = vd.grad.double().cpu() @ P if P is not None else vd.grad.double().cpu()
+    assert qd.grad.dtype == q.dtype and vd.grad.dtype == v.dtype
+    assert rel_err(dq, gold["dq"]) < tol
+    assert rel_err(dv, gold["dv"]) < tol
+    scale = (oracle["g"].abs() * oracle["clip"].abs().double()).sum().item() / T
+    assert abs(m.temperature.grad.item() - float(gold["dT"])) < (1e-4 if fp32 else 2e-2) * scale
+
+    # (4) and vs the fp64 oracle (tighter: only output rounding separates them)
+    assert abs(con.item() - oracle["loss"].item()) < ctol * abs(oracle["loss"].item())
+    otol = 1e-5 if fp32 else 4e-3          # bf16 outputs: one rounding of each gradient element
+    assert rel_err(qd.grad.double().cpu(), oracle["dq"]) < otol
+    assert rel_err(vd.grad.double().cpu(), oracle["dv"]) < otol
+    assert abs(m.temperature.grad.item() - oracle["dT"].item()) < 1e-5 * scale
+
+    # (5) statistics dictionary: same keys as the reference, values within tolerance
+    keys = [str(k) for k in gold["stats_keys"]]
+    assert sorted(stats.keys()) == keys
+    sc = max(abs(float(x)) for x in gold["stats_vals"])
+    stol = 1e-2 if (case.dtype == "bf16" and case.kind == "av") else 1e-4
+    for k, ref in zip(keys, gold["stats_vals"]):
+        assert abs(stats[k] - float(ref)) <= stol * sc, k
+
+
+def _near_tie_report(q, v, T, idx_a, idx_b):
+    """For argmax disagreements between two accumulation orders, check each is a genuine
+    near-tie: the exact (fp64) similarities of the two candidates differ by < 2 bf16 ulps."""
+    bad = (idx_a != idx_b).nonzero()
+    worst = 0.0
+    for i, j, a in bad.tolist():
+        s = (q[i, a].double() @ v[j].double().t()) * T
+        x, y = s[idx_a[i, j, a]].item(), s[idx_b[i, j, a]].item()
+        worst = max(worst, abs(x - y) / max(abs(x), 1e-30))
+    return len(bad), worst
+
+
+@pytest.mark.parametrize("flags", [0, FWD_1CTA])
+def test_tensor_core_vs_oracle_mid_size(flags):
+    """B=24 x 250 x 256 x 512: tcgen05 argmax vs the CPU oracle.  Different fp32 accumulation
+    orders can flip a bf16 rounding on an exact-to-the-ulp tie; every disagreement must be such
+    a near-tie and they must be rare."""
+    from triad_b200 import ops
+    B, Nq, Nv, D = 24, 250, 256, 512
+    q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=77)
+    ref = O.maxmean_forward(q, v, 1.5)
+    scale = ops.row_scale(None, B, Nq, torch.device("cuda"))
+    Tt = torch.tensor(1.5, device="cuda")
+    clip, idx = ops.maxmean_fwd(q.cuda(), v.cuda(), scale, Tt, flags=flags, check_watchdog=True)
+    idx = idx.view(B, B, Nq).permute(1, 0, 2).cpu().long()
+    n_bad, worst = _near_tie_report(q, v, 1.5, idx, ref["idx"])
+    assert n_bad <= 1e-4 * idx.numel(), n_bad
+    assert worst < 2 ** -7, worst
+    assert rel_err(clip.cpu(), ref["clip"]) < 1e-5
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg 2 (B=256, 250 frames x 256 patches, D=512, bf16) — properties that do not
+    need the (16.8 GB) dense tensor."""
+    from triad_b200 import ops
+    B, Nq, Nv, D = 256, 250, 256, 512
+    q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=1234)
+    qd, vd = q.cuda(), v.cuda()
+    dev = qd.device
+    scale = ops.row_scale(None, B, Nq, dev)
+    Tt = torch.tensor(1.5, device=dev)
+    clip, idx = ops.maxmean_fwd(qd, vd, scale, Tt, check_watchdog=True)
+
+    # (a) run-to-run determinism, bit for bit
+    clip2, idx2 = ops.maxmean_fwd(qd, vd, scale, Tt)
+    assert torch.equal(clip, clip2) and torch.equal(idx, idx2)
+
+    # (b) tiling independence: a sub-batch of queries against a sub-set of images reproduces the
+    #     corresponding block: argmax bit-exactly (same arithmetic per element whatever the tile
+    #     schedule), clip up to the fp32 summation order of the per-group partial sums
+    qi, vj = slice(37, 37 + 19), slice(101, 101 + 50)
+    sub_scale = ops.row_scale(None, 19, Nq, dev)
+    clip_s, idx_s = ops.maxmean_fwd(qd[qi].contiguous(), vd[vj].contiguous(), sub_scale, Tt)
+    assert torch.allclose(clip_s, clip[qi, vj], rtol=2e-6, atol=0)
+    assert torch.equal(idx_s, idx.view(B, B, Nq)[vj, qi].reshape(50, 19 * Nq))
+
+    # (c) a slice against the CPU oracle (argmax bit-exact up to certified near-ties)
+    ref = O.maxmean_forward(q[:6], v, 1.5)
+    got = idx.view(B, B, Nq)[:, :6].permute(1, 0, 2).cpu().long()
+    n_bad, worst = _near_tie_report(q[:6], v, 1.5, got, ref["idx"])
+    assert n_bad <= 1e-4 * got.numel() and worst < 2 ** -7
+    assert rel_err(clip[:6].cpu(), ref["clip"]) < 1e-5
+
+    # (d) permutation equivariance: permuting the images permutes clip columns exactly
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
+    clip_p, _ = ops.maxmean_fwd(qd, vd[perm].contiguous(), scale, Tt)
+    assert torch.equal(clip_p, clip[:, perm])
+
+    # (e) loss + closed-form gradient identities: rows/cols of g sum to ~0 around the diagonal term
+    row_lse, col_part = ops.infonce_partial(clip, B, 0)
+    g, sums = ops.infonce_finish(clip, B, 0, row_lse, col_part.reshape(1, 2, B))
+    nce = O.infonce(clip.cpu())
+    assert abs(sums[0].item() / (2 * B) - nce["loss"].item()) < 1e-6 * nce["loss"].item()
+    assert rel_err(g.cpu(), nce["g"]) < 1e-5
+    assert g.sum(dim=1).abs().max().item() < 1e-6 and g.double().sum().abs().item() < 1e-7
+
+    # (f) backward: linear in g (exactly, for power-of-two scaling), and checked against the oracle
+    #     on a slice of queries / images
+    dq, dv, dT = ops.maxmean_bwd(qd, vd, idx, g, clip, scale, Tt)
+    dq2, dv2, dT2 = ops.maxmean_bwd(qd, vd, idx, g * 2, clip, scale, Tt)
+    assert torch.equal(dq2.float(), dq.float() * 2) and torch.equal(dv2.float(), dv.float() * 2)
+    # independent fp64 evaluation of the gather / scatter formulas with plain torch indexing (test-only)
+    g64, q64, v64 = g.double(), qd.double().view(B * Nq, D), vd.double().view(B * Nv, D)
+    idx_l = idx.long()                                           # [Bv, M]
+    for i in (0, 100, 255):
+        rows = torch.arange(i * Nq, (i + 1) * Nq, device=dev)
+        flat = idx_l[:, rows] + (torch.arange(B, device=dev) * Nv)[:, None]          # (Bv,Nq)
+        want = 1.5 * scale[rows].double()[:, None] * (g64[i][:, None, None] * v64[flat]).sum(dim=0)
+        assert rel_err(dq[i].cpu(), want.cpu()) < 4e-3
+    w_rows = 1.5 * scale.double()[None, :] * g64.t().repeat_interleave(Nq, dim=1)      # [Bv, M]
+    for j in (0, 77, 255):
+        want = torch.zeros(Nv, D, dtype=torch.float64, device=dev)
+        want.index_add_(0, idx_l[j], w_rows[j][:, None] * q64)
+        assert rel_err(dv[j].cpu(), want.cpu()) < 4e-3
+    ssum = (g.abs() * clip.abs()).double().sum().item() / 1.5
+    assert abs(dT.item() - ((g64 * clip.double()).sum() / 1.5).item()) < 1e-5 * ssum
+
+
+def test_masked_text_shape_cfg3_slice():
+    """cfg 3 flavour: 77 text tokens with ragged right-padded masks (n_i in [8,77])."""
+    B, Nq, Nv, D = 48, 77, 256, 512
+    q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=31, masked=True, min_len=8)
+    m = _model(1.5)
+    qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    clip, tok = m.compute_all_similarities_tv(qd, vd, mask.cuda())
+    loss, stats = m.compute_contrastive_loss_tv(clip, tok)
+    loss.backward()
+    ref = O.contrastive_step_closed_form(q, v, 1.5, mask)
+    n_bad, worst = _near_tie_report(q, v, 1.5, tok.argmax().cpu(), ref["idx"])
+    assert n_bad <= 1e-4 * ref["idx"].numel() and worst < 2 ** -7
+    assert rel_err(tok.clip.detach().cpu(), ref["clip"]) < 1e-5
+    assert abs(loss.item() - ref["loss"].item()) < 1e-5 * ref["loss"].item()
+    assert rel_err(qd.grad.cpu(), ref["dq"]) < 4e-3 and rel_err(vd.grad.cpu(), ref["dv"]) < 4e-3
+    # padded tokens receive exactly zero gradient (mask multiplies their maxima by 0, model.py:510)
+    assert qd.grad[mask.cuda() == 0].abs().max().item() == 0.0
+
+
+def test_retrieval_against_reference_goldens():
+    from triad_b200 import retrieval as R
+    gold = load_golden("retrieval")
+    g = torch.Generator().manual_seed(77)
+    row = 0
+    for n, (nq, nv, d) in enumerate(gold["agg_shapes"].tolist()):
+        qf = torch.randn(nq, d, generator=g)
+        vf = torch.randn(nv, d, generator=g)
+        if n != 1:
+            qf = torch.nn.functional.normalize(qf, dim=1)
+            vf = torch.nn.functional.normalize(vf, dim=1)
+        for T in gold["agg_T"].tolist():
+            ref = gold["agg_vals"][row]
+            row += 1
+            got = [R.aggregator_av_a2v(qf.cuda(), vf.cuda(), T), R.aggregator_av_v2a(qf.cuda(), vf.cuda(), T),
+                   R.aggregator_tv_t2v(qf.cuda(), vf.cuda(), T), R.aggregator_tv_v2t(qf.cuda(), vf.cuda(), T)]
+            assert np.allclose(got, ref, rtol=1e-4, atol=1e-6), (n, T, got, ref)
+    rec = R.compute_recall_at_k(gold["recall_sim"])
+    assert np.allclose([rec["r1"], rec["r5"], rec["r10"], rec["r20"]], gold["recall_vals"])
+
+
+def test_retrieval_matrix_topk_and_simmat():
+    from triad_b200 import retrieval as R
+    g = torch.Generator().manual_seed(5)
+    N = 12
+    qs = [torch.nn.functional.normalize(torch.randn(int(n), 64, generator=g), dim=1) for n in torch.randint(3, 20, (N,), generator=g)]
+    vs = [torch.nn.functional.normalize(torch.randn(40, 64, generator=g), dim=1) for _ in range(N)]
+    for direction, name in ((0, "q2v"), (1, "v2q")):
+        sim = R.pairwise_similarity(qs, vs, 0.7, direction).cpu()
+        ref = torch.tensor([[O.aggregate_pair(qs[i], vs[j], 0.7, name) for j in range(N)] for i in range(N)])
+        assert torch.allclose(sim, ref, rtol=1e-4, atol=1e-6)
+    m = R.metrics_from_features(qs, vs, 0.7, "cuda", "av")
+    assert sorted(m) == sorted([f"{a}_r{k}" for a in ("A->V", "V->A") for k in (1, 5, 10, 20)])
+    # top-k over a bf16 gallery (cfg 5 flavour, small): ids and scores vs torch.topk of the oracle scores
+    q = torch.nn.functional.normalize(torch.randn(77, 512, generator=g), dim=1).bfloat16()
+    gal = torch.nn.functional.normalize(torch.randn(300, 256, 512, generator=g), dim=2).bfloat16()
+    s, ids = R.retrieve_topk(q.cuda(), gal.cuda(), 1.5, 10)
+    scores = R._scores(q.cuda(), gal.cuda(), 1.5, 0)
+    ts, ti = torch.topk(scores, 10)
+    assert torch.equal(ids.long(), ti) and torch.equal(s, ts)
+    ref0 = O.aggregate_pair(q.float(), gal[int(ids[0])].float(), 1.5, "q2v")
+    assert abs(s[0].item() - ref0) < 1e-2 * abs(ref0)
+    # compute_similarity_matrix
+    gold = load_golden("retrieval")
+    g2 = torch.Generator().manual_seed(77)
+    for (nq, nv, d) in gold["agg_shapes"].tolist():
+        torch.randn(nq, d, generator=g2); torch.randn(nv, d, generator=g2)
+    torch.randn(60, 60, generator=g2)
+    f1 = torch.randn(3, 9, 32, generator=g2)
+    f2 = torch.randn(3, 17, 32, generator=g2)
+    out = _model(1.5).compute_similarity_matrix(f1.cuda(), f2.cuda()).cpu().numpy()
+    assert np.allclose(out, gold["simmat"], atol=1e-5)
+
+
+def test_errors_are_loud():
+    from triad_b200 import ops
+    from triad_b200._lib import TriadError
+    m = _model(1.5)
+    with pytest.raises(RuntimeError):
+        m.compute_all_similarities_av(torch.randn(2, 3, 64), torch.randn(2, 5, 64))       # CPU tensors
+    with pytest.raises(TypeError):
+        m.compute_all_similarities_av(torch.randn(2, 3, 64).cuda().half(), torch.randn(2, 5, 64).cuda().half())
+    with pytest.raises(TriadError):
+        m.compute_all_similarities_av(torch.randn(2, 3, 60).cuda(), torch.randn(2, 5, 60).cuda())  # D % 8

@@ -129,12 +129,15 @@ dq_gather_kernel(const T* __restrict__ v, const IdxT* __restrict__ idx, const fl
 }
 
 // ---------------------------------------------------------------------------------------
-// dv: one CTA = one image x one D-slice; fp32 accumulators for every patch live in shared
-// memory; warps stream all M rows (idx[j][:] is contiguous) and add w*q[r,slice] into the
-// winning patch's accumulator.
+// dv (baseline): one CTA = one image x one D-slice of 32*kDvWarps dims; fp32 accumulators for
+// every patch live in shared memory.  Each warp owns 32 dims (one per lane) of ALL patches and
+// streams ALL M rows, so no two threads ever touch the same accumulator: no atomics, and the
+// summation order (row order) is fixed => deterministic.
 // ---------------------------------------------------------------------------------------
+constexpr int kDvWarps = 4;
+
 template <typename T, typename IdxT, typename OutT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDvWarps * 32)
 dv_scatter_kernel(const T* __restrict__ q, const IdxT* __restrict__ idx, const float* __restrict__ g,
                   const float* __restrict__ row_scale, const float* __restrict__ Tptr,
                   int M, int Bv, int Nq, int Nv, int D, int DS, OutT* __restrict__ dv) {
@@ -145,12 +148,13 @@ dv_scatter_kernel(const T* __restrict__ q, const IdxT* __restrict__ idx, const f
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float Tval = *Tptr;
 
-    for (int t = threadIdx.x; t < Nv * DS; t += 256) acc_s[t] = 0.f;
+    for (int t = threadIdx.x; t < Nv * DS; t += kDvWarps * 32) acc_s[t] = 0.f;
     __syncthreads();
 
     const IdxT* idxj = idx + (size_t)j * M;
-    // each warp takes 32 rows at a time: lane l prefetches row (base+l)'s patch and weight
-    for (int base = warp * 32; base < M; base += 8 * 32) {
+    const int dcol = warp * 32 + lane;               // this thread's column inside the slice
+    const bool active = dcol < DS;
+    for (int base = 0; base < M; base += 32) {
         const int r = base + lane;
         int p = 0; float w = 0.f;
         if (r < M) {
@@ -158,19 +162,16 @@ dv_scatter_kernel(const T* __restrict__ q, const IdxT* __restrict__ idx, const f
             w = Tval * row_scale[r] * g[(size_t)(r / Nq) * Bv + j];
         }
         const int nrow = min(32, M - base);
+        const T* src = q + (size_t)base * D + d0 + dcol;
         for (int l = 0; l < nrow; ++l) {
             const float wl = __shfl_sync(0xffffffffu, w, l);
             const int pl = __shfl_sync(0xffffffffu, p, l);
-            if (wl == 0.f) continue;                 // masked token rows contribute nothing
-            const T* src = q + (size_t)(base + l) * D + d0;
-            float* dst = acc_s + (size_t)pl * DS;
-            for (int d = lane; d < DS; d += 32)
-                atomicAdd(dst + d, wl * (float)src[d]);
+            if (wl != 0.f && active) acc_s[pl * DS + dcol] += wl * (float)src[(size_t)l * D];
         }
     }
     __syncthreads();
     OutT* out = dv + (size_t)j * Nv * D + d0;
-    for (int t = threadIdx.x; t < Nv * DS; t += 256) {
+    for (int t = threadIdx.x; t < Nv * DS; t += kDvWarps * 32) {
         const int p = t / DS, d = t % DS;
         out[(size_t)p * D + d] = (OutT)acc_s[t];
     }
@@ -198,7 +199,7 @@ dT_kernel(const float* __restrict__ g, const float* __restrict__ clip, size_t n,
 static int pick_dv_slice(int Nv, int D) {
     // largest slice (multiple of 8 dividing D) whose accumulators fit ~160 KB of shared memory
     int best = 0;
-    for (int ds = 8; ds <= D; ds += 8)
+    for (int ds = 8; ds <= D && ds <= 32 * kDvWarps; ds += 8)
         if (D % ds == 0 && (size_t)Nv * ds * 4 <= 160 * 1024) best = ds;
     return best;
 }
@@ -233,11 +234,11 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
         if (dv_f32 || sizeof(T) == 4) {
             auto kern = dv_scatter_kernel<T, IdxT, float>;
             TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, 256, smem, st>>>((const T*)q, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, DS, (float*)dv);
+            kern<<<grid, kDvWarps * 32, smem, st>>>((const T*)q, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, DS, (float*)dv);
         } else {
             auto kern = dv_scatter_kernel<T, IdxT, T>;
             TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, 256, smem, st>>>((const T*)q, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, DS, (T*)dv);
+            kern<<<grid, kDvWarps * 32, smem, st>>>((const T*)q, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, DS, (T*)dv);
         }
         TRIAD_LAUNCH_CHECK("dv_scatter_kernel");
     }

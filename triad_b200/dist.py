@@ -1,0 +1,134 @@
+"""Row-sharded contrastive step across the GPUs of one node.
+
+The reference is single-GPU.  The B x B clip matrix shards naturally by rows: rank r owns
+queries and images [r*Bl,(r+1)*Bl).  One exchange each way:
+
+  forward   all-gather(V)                     -> every rank scores its queries against ALL images
+            all-gather(column (max,sumexp))   -> 2*B floats per rank, completes the column softmax
+            all-gather(8 fp64 sums)           -> loss and the similarity statistics
+  backward  reduce-scatter(dV partial, fp32)  -> each rank receives the gradient of its own images
+            (dQ is local; dT is a sum of the per-rank  sum g*clip  already in the 8 sums)
+
+There is no other data-path collective; per-rank work is (B/W) x B pairs.  Collectives go through
+torch.distributed (NCCL over NVLink/NVSwitch on the GPU box; gloo in the CPU tests, where the
+four kernel entry points are injected by the test — the product binding below is CUDA-only).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class CudaKernels:
+    """The product binding: the C-ABI ops."""
+
+    def row_scale(self, mask, Bq, Nq, device):
+        from . import ops
+        return ops.row_scale(mask, Bq, Nq, device)
+
+    def maxmean_fwd(self, q, v, scale, T):
+        from . import ops
+        return ops.maxmean_fwd(q, v, scale, T, want_idx=True)
+
+    def infonce_partial(self, clip_rows, B, row0):
+        from . import ops
+        return ops.infonce_partial(clip_rows, B, row0)
+
+    def infonce_finish(self, clip_rows, B, row0, row_lse, col_parts):
+        from . import ops
+        return ops.infonce_finish(clip_rows, B, row0, row_lse, col_parts)
+
+    def maxmean_bwd(self, q, v, idx, g, clip, scale, T):
+        from . import ops
+        dq, dv, _ = ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True,
+                                    need_dT=False, dv_f32=True)
+        return dq, dv
+
+
+def _all_gather(x: torch.Tensor, W: int, group) -> torch.Tensor:
+    """all-gather along a new leading dim ([W, *x.shape]); flat views keep every backend happy."""
+    x = x.contiguous()
+    out = torch.empty((W,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out.view(-1), x.view(-1), group=group)
+    return out
+
+
+def _reduce_scatter_rows(x: torch.Tensor, W: int, r: int, group) -> torch.Tensor:
+    """sum over ranks of x ([W*n, ...]), returning this rank's n rows.  NCCL: one reduce-scatter
+    over NVLink; gloo (CPU tests) has no reduce-scatter, so all-reduce and slice."""
+    n = x.shape[0] // W
+    if dist.get_backend(group) == "gloo":
+        y = x.contiguous().clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y[r * n:(r + 1) * n].contiguous()
+    out = torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.reduce_scatter_tensor(out.view(-1), x.contiguous().view(-1), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def stats_from_all_sums(all_sums: torch.Tensor, B: int, prefix: str) -> Dict[str, float]:
+    """Combine the per-rank fp64 sums ([W,8]) into the reference's six statistics
+    (model.py:435-450): everything adds except the hardest negative, which is a max."""
+    from .model import _stats_from_sums
+    s = all_sums.sum(dim=0)
+    s[5] = all_sums[:, 5].max()
+    return _stats_from_sums(s, B, prefix)
+
+
+def sharded_contrastive_step(q_local: torch.Tensor, v_local: torch.Tensor, temperature: torch.Tensor,
+                             mask_local: Optional[torch.Tensor] = None, group=None, kernels=None,
+                             need_grads: bool = True) -> Dict[str, torch.Tensor]:
+    """One forward(+backward) of max-mean similarity + symmetric InfoNCE over a row-sharded batch.
+
+    q_local (Bl,Nq,D), v_local (Bl,Nv,D): this rank's queries and images.  Returns
+    {loss (global, fp32 scalar), all_sums [W,8] fp64, clip_rows (Bl,B), dq (Bl,Nq,D), dv (Bl,Nv,D),
+     dT (fp32 scalar)} — gradients of the GLOBAL loss w.r.t. this rank's shards."""
+    k = kernels if kernels is not None else CudaKernels()
+    W = dist.get_world_size(group) if dist.is_initialized() else 1
+    r = dist.get_rank(group) if dist.is_initialized() else 0
+    Bl, Nq, D = q_local.shape
+    Nv = v_local.shape[1]
+    B = Bl * W
+    dev = q_local.device
+    q_local, v_local = q_local.contiguous(), v_local.contiguous()
+    T = temperature.detach().to(device=dev, dtype=torch.float32).reshape(())
+
+    v_all = _all_gather(v_local, W, group).view(B, Nv, D) if W > 1 else v_local
+
+    scale = k.row_scale(mask_local, Bl, Nq, dev)
+    clip_rows, idx = k.maxmean_fwd(q_local, v_all, scale, T)             # (Bl,B), [B, Bl*Nq]
+    row_lse, col_part = k.infonce_partial(clip_rows, B, r * Bl)          # (Bl,), (2,B)
+    col_parts = _all_gather(col_part, W, group) if W > 1 else col_part.reshape(1, 2, B)
+    g, sums = k.infonce_finish(clip_rows, B, r * Bl, row_lse, col_parts)  # (Bl,B), (8,) fp64
+    all_sums = _all_gather(sums, W, group) if W > 1 else sums.reshape(1, 8)
+    loss = (all_sums[:, 0].sum() / (2 * B)).to(torch.float32)
+    out = {"loss": loss, "all_sums": all_sums, "clip_rows": clip_rows, "B": B}
+    if not need_grads:
+        return out
+
+    dq, dv_partial = k.maxmean_bwd(q_local, v_all, idx, g, clip_rows, scale, T)   # dv_partial (B,Nv,D) fp32
+    dv32 = _reduce_scatter_rows(dv_partial, W, r, group) if W > 1 else dv_partial
+    out["dq"] = dq
+    out["dv"] = dv32.to(v_local.dtype)
+    out["dT"] = (all_sums[:, 6].sum() / T.double()).to(torch.float32)
+    return out
+
+
+class ShardedContrastiveLoss(torch.autograd.Function):
+    """Autograd face of sharded_contrastive_step: the forward computes the loss AND the gradients
+    (the saved argmax indices never outlive the call); backward scales them by the incoming grad."""
+
+    @staticmethod
+    def forward(ctx, q_local, v_local, temperature, mask_local, group):
+        out = sharded_contrastive_step(q_local, v_local, temperature, mask_local, group)
+        ctx.save_for_backward(out["dq"], out["dv"], out["dT"])
+        ctx.t_like = temperature
+        ctx.mark_non_differentiable(out["all_sums"])
+        return out["loss"], out["all_sums"]
+
+    @staticmethod
+    def backward(ctx, gl, _gs):
+        dq, dv, dT = ctx.saved_tensors
+        return dq * gl.to(dq.dtype), dv * gl.to(dv.dtype), (dT * gl).reshape(ctx.t_like.shape).to(ctx.t_like.dtype), None, None

@@ -57,6 +57,58 @@ class TokenSims:
         return f"TokenSims(shape={tuple(self.shape)}, dtype={self.dtype}, device={self.device}, fused)"
 
 
+class LazyStats(dict):
+    """The statistics dictionary of model.py:463-470, filled on first access.
+
+    The reference pays five ``.item()`` device->host syncs per loss call to build this dict even
+    when nobody looks at it.  Here the six values live in one small device tensor until a key is
+    actually read (wandb logging, prints); the training step itself stays asynchronous, so the
+    backward kernels can be queued while the forward is still running."""
+
+    def __init__(self, sums: torch.Tensor, B: int, prefix: str):
+        super().__init__()
+        self._pending = (sums, B, prefix)
+
+    def _fill(self):
+        if self._pending is not None:
+            sums, B, prefix = self._pending
+            self._pending = None
+            super().update(_stats_from_sums(sums, B, prefix))
+
+    def __getitem__(self, k):
+        self._fill(); return super().__getitem__(k)
+
+    def __iter__(self):
+        self._fill(); return super().__iter__()
+
+    def __len__(self):
+        self._fill(); return super().__len__()
+
+    def __contains__(self, k):
+        self._fill(); return super().__contains__(k)
+
+    def keys(self):
+        self._fill(); return super().keys()
+
+    def values(self):
+        self._fill(); return super().values()
+
+    def items(self):
+        self._fill(); return super().items()
+
+    def get(self, k, default=None):
+        self._fill(); return super().get(k, default)
+
+    def __repr__(self):
+        self._fill(); return super().__repr__()
+
+    def __eq__(self, other):
+        self._fill(); return super().__eq__(other)
+
+    def copy(self):
+        self._fill(); return dict(self)
+
+
 def _stats_from_sums(sums: torch.Tensor, B: int, prefix: str) -> Dict[str, float]:
     """model.py:435-450 / :553-568 from the kernel's fp64 sums; ONE device->host copy instead of
     the reference's five .item() calls."""
@@ -109,7 +161,7 @@ class TriadSimilarityMixin:
     def _contrastive(self, clip_sims, token_sims, prefix) -> Tuple[torch.Tensor, Dict[str, float]]:
         clip = token_sims.clip if isinstance(token_sims, TokenSims) else clip_sims
         loss, sums = ops.SymmetricInfoNCE.apply(clip)
-        return loss, _stats_from_sums(sums, clip.shape[0], prefix)
+        return loss, LazyStats(sums, clip.shape[0], prefix)
 
     def _temperature_calibration(self) -> torch.Tensor:
         """20 * relu(-log T)^2 — the l_cal term of model.py:420-427 (a scalar on the parameter)."""
