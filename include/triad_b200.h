@@ -17,10 +17,11 @@
  *   - M = Bq*Nq is the number of query-token rows ("rows" below).
  *
  * Layouts the library defines (the reference never materialises them on this path):
- *   idx   : [Bv][M]  uint8 when Nv <= 256 else uint16 — idx[j][i*Nq+a] = argmax_p S[i,j,a,p],
- *           first index among ties (torch.max, model.py:389).  image-major so that one
- *           128-row tile writes 128 contiguous bytes and the dV pass reads one image's
- *           winners contiguously.
+ *   idx   : [Bv][Bq][nq_pad]  uint8 when Nv <= 256 else uint16, nq_pad = Nq rounded up to 16 —
+ *           idx[j][i][a] = argmax_p S[i,j,a,p], first index among ties (torch.max, model.py:389);
+ *           entries a >= Nq are never written or read.  Image-major so that the dV pass reads one
+ *           image's winners contiguously; the per-query padding keeps every query's run 16-byte
+ *           aligned for the vector loads of the dQ pass.
  *   row_scale : [M] fp32 — weight of token row r in its query's (masked) mean:
  *           1/Nq (model.py:391) or mask/clamp(sum mask,1e-7) (model.py:509-512).
  */

@@ -20,7 +20,10 @@ class OracleKernels:
             m, ix = torch.max(s, dim=2)
             idx[i], rowmax[i] = ix, m.float()
         clip = (rowmax * scale.view(Bq, 1, Nq)).sum(dim=2)
-        return clip, idx.permute(1, 0, 2).reshape(Bv, Bq * Nq).to(torch.uint8 if v.shape[1] <= 256 else torch.int32)
+        pad = (Nq + 15) // 16 * 16                       # library layout: [Bv][Bq][nq_pad]
+        lib = torch.zeros(Bv, Bq, pad, dtype=torch.uint8 if v.shape[1] <= 256 else torch.int32)
+        lib[:, :, :Nq] = idx.permute(1, 0, 2).to(lib.dtype)
+        return clip, lib.reshape(Bv, Bq * pad)
 
     def infonce_partial(self, clip_rows, B, row0):
         row_lse = torch.logsumexp(clip_rows, dim=1)
@@ -47,6 +50,7 @@ class OracleKernels:
     def maxmean_bwd(self, q, v, idx, g, clip, scale, T):
         Bq, Nq, D = q.shape
         Bv, Nv, _ = v.shape
-        idx_ref = idx.to(torch.int64).view(Bv, Bq, Nq).permute(1, 0, 2)
+        pad = (Nq + 15) // 16 * 16
+        idx_ref = idx.to(torch.int64).view(Bv, Bq, pad)[:, :, :Nq].permute(1, 0, 2)
         dq, dv, _ = O.maxmean_backward(q, v, idx_ref, g, float(T), scale.view(Bq, Nq), clip)
         return dq.to(q.dtype), dv.float()

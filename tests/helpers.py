@@ -20,13 +20,14 @@ def check_inputs_reproduce(gold, q, v):
     assert abs((v.double() ** 2).sum().item() - float(gold["in_v_sq"])) < 1e-9
 
 
+def _as64(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(device="cpu", dtype=torch.float64).reshape(-1)
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64).reshape(-1)
+
+
 def rel_err(a, b):
-    a = torch.as_tensor(np.asarray(a), dtype=torch.float64).reshape(-1)
-    b = torch.as_tensor(np.asarray(b), dtype=torch.float64).reshape(-1)
+    a, b = _as64(a), _as64(b)
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
 
-def idx_mismatch_report(idx, idx_ref, rowmax_exact, tol_ulp_bf16=True):
-    """Count argmax mismatches and classify each as a near-tie: rowmax_exact is the fp32
-    (un-rounded-to-bf16) token similarity tensor slice accessor, see callers."""
-    raise NotImplementedError

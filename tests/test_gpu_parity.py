@@ -65,7 +65,11 @@ def test_golden_parity(case, flags):
     assert clip.dtype == (torch.bfloat16 if bool(gold["clip_is_bf16"]) else torch.float32)
     assert rel_err(clip.float().cpu(), gold["clip"]) < tol
     oracle = O.contrastive_step_closed_form(q, v, T, mask)
-    ctol = 2e-6 if fp32 else 1e-5         # fp32 clip vs oracle fp32 clip (a flipped bf16 rounding moves one row max by 1 ulp)
+    # fp32 clip vs the oracle's fp32 clip.  bf16: the tensor core and the CPU accumulate the 512-term dot
+    # products in different orders, so an accumulator that sits on a bf16 rounding boundary can round the
+    # other way: that moves ONE row maximum by one bf16 ulp (2^-8 relative), i.e. one clip element by
+    # ~2^-8/Nq.  A handful of such flips gives ~1e-5 norm-wise; the north star's bound is 1e-2.
+    ctol = 2e-6 if fp32 else 5e-5
     assert rel_err(tok.clip.detach().cpu(), oracle["clip"]) < ctol
 
     # (3) loss and gradients vs the reference
@@ -119,11 +123,11 @@ def test_tensor_core_vs_oracle_mid_size(flags):
     scale = ops.row_scale(None, B, Nq, torch.device("cuda"))
     Tt = torch.tensor(1.5, device="cuda")
     clip, idx = ops.maxmean_fwd(q.cuda(), v.cuda(), scale, Tt, flags=flags, check_watchdog=True)
-    idx = idx.view(B, B, Nq).permute(1, 0, 2).cpu().long()
+    idx = ops.idx_to_reference_layout(idx, B, Nq).cpu()
     n_bad, worst = _near_tie_report(q, v, 1.5, idx, ref["idx"])
     assert n_bad <= 1e-4 * idx.numel(), n_bad
     assert worst < 2 ** -7, worst
-    assert rel_err(clip.cpu(), ref["clip"]) < 1e-5
+    assert rel_err(clip.cpu(), ref["clip"]) < 5e-5
 
 
 def test_full_size_properties_cfg2():
@@ -140,7 +144,8 @@ def test_full_size_properties_cfg2():
 
     # (a) run-to-run determinism, bit for bit
     clip2, idx2 = ops.maxmean_fwd(qd, vd, scale, Tt)
-    assert torch.equal(clip, clip2) and torch.equal(idx, idx2)
+    assert torch.equal(clip, clip2)
+    assert torch.equal(ops.idx_to_reference_layout(idx, B, Nq), ops.idx_to_reference_layout(idx2, B, Nq))
 
     # (b) tiling independence: a sub-batch of queries against a sub-set of images reproduces the
     #     corresponding block: argmax bit-exactly (same arithmetic per element whatever the tile
@@ -149,14 +154,15 @@ def test_full_size_properties_cfg2():
     sub_scale = ops.row_scale(None, 19, Nq, dev)
     clip_s, idx_s = ops.maxmean_fwd(qd[qi].contiguous(), vd[vj].contiguous(), sub_scale, Tt)
     assert torch.allclose(clip_s, clip[qi, vj], rtol=2e-6, atol=0)
-    assert torch.equal(idx_s, idx.view(B, B, Nq)[vj, qi].reshape(50, 19 * Nq))
+    idx_ref = ops.idx_to_reference_layout(idx, B, Nq)            # (Bq,Bv,Nq)
+    assert torch.equal(ops.idx_to_reference_layout(idx_s, 19, Nq), idx_ref[qi, vj])
 
     # (c) a slice against the CPU oracle (argmax bit-exact up to certified near-ties)
     ref = O.maxmean_forward(q[:6], v, 1.5)
-    got = idx.view(B, B, Nq)[:, :6].permute(1, 0, 2).cpu().long()
+    got = idx_ref[:6].cpu()
     n_bad, worst = _near_tie_report(q[:6], v, 1.5, got, ref["idx"])
     assert n_bad <= 1e-4 * got.numel() and worst < 2 ** -7
-    assert rel_err(clip[:6].cpu(), ref["clip"]) < 1e-5
+    assert rel_err(clip[:6].cpu(), ref["clip"]) < 5e-5
 
     # (d) permutation equivariance: permuting the images permutes clip columns exactly
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
@@ -169,7 +175,7 @@ def test_full_size_properties_cfg2():
     nce = O.infonce(clip.cpu())
     assert abs(sums[0].item() / (2 * B) - nce["loss"].item()) < 1e-6 * nce["loss"].item()
     assert rel_err(g.cpu(), nce["g"]) < 1e-5
-    assert g.sum(dim=1).abs().max().item() < 1e-6 and g.double().sum().abs().item() < 1e-7
+    assert g.double().sum().abs().item() < 1e-7          # sum(P) = sum(Q) = B, so sum(g) = (B + B - 2B)/(2B) = 0
 
     # (f) backward: linear in g (exactly, for power-of-two scaling), and checked against the oracle
     #     on a slice of queries / images
@@ -178,7 +184,7 @@ def test_full_size_properties_cfg2():
     assert torch.equal(dq2.float(), dq.float() * 2) and torch.equal(dv2.float(), dv.float() * 2)
     # independent fp64 evaluation of the gather / scatter formulas with plain torch indexing (test-only)
     g64, q64, v64 = g.double(), qd.double().view(B * Nq, D), vd.double().view(B * Nv, D)
-    idx_l = idx.long()                                           # [Bv, M]
+    idx_l = idx_ref.permute(1, 0, 2).reshape(B, B * Nq)           # [Bv, M]
     for i in (0, 100, 255):
         rows = torch.arange(i * Nq, (i + 1) * Nq, device=dev)
         flat = idx_l[:, rows] + (torch.arange(B, device=dev) * Nv)[:, None]          # (Bv,Nq)
@@ -205,7 +211,7 @@ def test_masked_text_shape_cfg3_slice():
     ref = O.contrastive_step_closed_form(q, v, 1.5, mask)
     n_bad, worst = _near_tie_report(q, v, 1.5, tok.argmax().cpu(), ref["idx"])
     assert n_bad <= 1e-4 * ref["idx"].numel() and worst < 2 ** -7
-    assert rel_err(tok.clip.detach().cpu(), ref["clip"]) < 1e-5
+    assert rel_err(tok.clip.detach().cpu(), ref["clip"]) < 5e-5      # see ctol in test_golden_parity
     assert abs(loss.item() - ref["loss"].item()) < 1e-5 * ref["loss"].item()
     assert rel_err(qd.grad.cpu(), ref["dq"]) < 4e-3 and rel_err(vd.grad.cpu(), ref["dv"]) < 4e-3
     # padded tokens receive exactly zero gradient (mask multiplies their maxima by 0, model.py:510)

@@ -55,7 +55,8 @@ def stage_simt():
         md = mask.cuda() if mask is not None else None
         clip, ix, _, _ = _fwd(qd, vd, T, md, flags=1)
         B, Nq = c.B, c.Nq
-        idx = ix.view(B, B, Nq).permute(1, 0, 2).cpu().to(torch.int64)
+        from triad_b200 import ops
+        idx = ops.idx_to_reference_layout(ix, B, Nq).cpu()
         bad = (idx != torch.from_numpy(gold["idx"].astype(np.int64))).sum().item()
         ref = O.maxmean_forward(q, v, T, mask)
         err = (clip.cpu() - ref["clip"]).abs().max().item()

@@ -17,7 +17,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libtriad_b200.so"
 
 SOURCES = ["capi.cu", "maxmean_simt.cu", "maxmean_tc.cu", "infonce.cu", "maxmean_bwd.cu", "retrieve.cu"]
-HEADERS = ["common.cuh", "triad_round.h", os.path.join("..", "..", "include", "triad_b200.h")]
+HEADERS = ["common.cuh", "ptx.cuh", "triad_round.h", os.path.join("..", "..", "include", "triad_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

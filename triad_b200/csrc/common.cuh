@@ -43,11 +43,16 @@ static inline PartLayout part_layout(int M, int Nq) {
     PartLayout p; p.G = ceil_div(M, 32); p.S = 31 / Nq + 2; return p;
 }
 
+// ---- argmax index layout ------------------------------------------------------------------
+// idx[j][i][a], a < nq_pad = Nq rounded up to 16: every query's run of winners starts 16-byte
+// aligned, so the backward can fetch 8 or 16 consecutive rows' winners with one vector load.
+static inline int nq_padded(int Nq) { return (Nq + 15) / 16 * 16; }
+
 // launchers implemented in the .cu files -------------------------------------------------
 int launch_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, cudaStream_t st);
 int launch_maxmean_simt(const void* q, const void* v, const float* row_scale, const float* T,
                         int inv_T, int M, int Bv, int Nq, int Nv, int D, int dtype,
-                        float* part, void* idx, cudaStream_t st);
+                        float* part, void* idx, cudaStream_t st);   // idx: [Bv][M/Nq][nq_padded(Nq)]
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
                       float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st);

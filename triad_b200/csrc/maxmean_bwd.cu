@@ -6,8 +6,12 @@
 //   dv[j,p,:] = sum_{r: idx[j][r]==p} T*row_scale[r]*g[i(r),j] * q[r,:]      (scatter)
 //   dT        = sum_ij g[i,j]*clip[i,j] / T
 //
-// Both passes are HBM/L2- and issue-bound CUDA-core work (2*D MACs per (row,image) pair, i.e.
-// 2/Nv of the forward's flops); they are not reshaped into one-hot GEMMs.
+// Both passes are L2- and issue-bound CUDA-core work (2*D MACs per (row,image) pair, i.e. 2/Nv
+// of the forward's flops); they are deliberately NOT reshaped into one-hot GEMMs (that would
+// cost a full forward each).  The scatter is turned into a gather: a stable per-image counting
+// sort of the rows by winning patch (one byte keys) gives every (image, patch) its list of
+// (row, weight) pairs, and a warp then accumulates that list in registers — no atomics, fixed
+// summation order, bit-reproducible.
 #include "common.cuh"
 
 namespace triad {
@@ -16,7 +20,7 @@ template <typename T> struct Vec16;            // one 16-byte chunk of a row
 template <> struct Vec16<__nv_bfloat16> {
     static constexpr int kElems = 8;
     __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -38,7 +42,7 @@ template <> struct Vec16<__nv_bfloat16> {
 template <> struct Vec16<float> {
     static constexpr int kElems = 4;
     __device__ static __forceinline__ void load(const float* p, float (&f)[4]) {
-        const float4 u = *reinterpret_cast<const float4*>(p);
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p));
         f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
     }
     __device__ static __forceinline__ void store(float* p, const float (&f)[4]) {
@@ -46,8 +50,21 @@ template <> struct Vec16<float> {
     }
 };
 
+// store E fp32 values as OutT (float or the input type)
+template <typename OutT, int E> struct StoreAs;
+template <int E> struct StoreAs<float, E> {
+    __device__ static __forceinline__ void put(float* p, const float (&f)[E]) {
+#pragma unroll
+        for (int c = 0; c < E; c += 4) *reinterpret_cast<float4*>(p + c) = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
+    }
+};
+template <> struct StoreAs<__nv_bfloat16, 8> {
+    __device__ static __forceinline__ void put(__nv_bfloat16* p, const float (&f)[8]) { Vec16<__nv_bfloat16>::store(p, f); }
+};
+
 // ---------------------------------------------------------------------------------------
-// dq: one CTA = one 32-row group; 8 warps x 4 rows; lanes own 16-byte chunks of D
+// dq (generic gather): one CTA = 32 consecutive token rows; 8 warps x 4 rows; lanes own
+// 16-byte chunks of D; winners and weights of 32 images at a time are staged in shared memory.
 // ---------------------------------------------------------------------------------------
 constexpr int kDqRows = 32;
 constexpr int kDqJ = 32;          // images staged per step
@@ -56,14 +73,23 @@ template <typename T, typename IdxT, int KCH>
 __global__ void __launch_bounds__(256)
 dq_gather_kernel(const T* __restrict__ v, const IdxT* __restrict__ idx, const float* __restrict__ g,
                  const float* __restrict__ row_scale, const float* __restrict__ Tptr,
-                 int M, int Bv, int Nq, int Nv, int D, T* __restrict__ dq) {
+                 int M, int Bv, int Nq, int Nv, int D, int nq_pad, T* __restrict__ dq) {
     constexpr int E = Vec16<T>::kElems;
     __shared__ IdxT idx_s[kDqJ][kDqRows];
     __shared__ float w_s[kDqRows][kDqJ + 1];
+    __shared__ int ioff_s[kDqRows];      // (i*nq_pad + a) of each row
+    __shared__ int iq_s[kDqRows];        // query index of each row
 
     const int row0 = blockIdx.x * kDqRows;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = D / E;
+    const size_t pitch = (size_t)(M / Nq) * nq_pad;
+    if (threadIdx.x < kDqRows) {
+        const int r = row0 + threadIdx.x;
+        const int qi = (r < M) ? r / Nq : 0;
+        iq_s[threadIdx.x] = qi;
+        ioff_s[threadIdx.x] = (r < M) ? qi * nq_pad + (r - qi * Nq) : -1;
+    }
 
     float acc[4][KCH][E];
 #pragma unroll
@@ -75,14 +101,14 @@ dq_gather_kernel(const T* __restrict__ v, const IdxT* __restrict__ idx, const fl
 
     for (int j0 = 0; j0 < Bv; j0 += kDqJ) {
         __syncthreads();
-        // stage idx[j0..j0+31][row0..row0+31] and the matching g entries
         for (int t = threadIdx.x; t < kDqJ * kDqRows; t += 256) {
             const int jj = t / kDqRows, rr = t % kDqRows;
-            const int j = j0 + jj, r = row0 + rr;
+            const int j = j0 + jj;
+            const int off = ioff_s[rr];
             IdxT p = 0; float w = 0.f;
-            if (j < Bv && r < M) {
-                p = idx[(size_t)j * M + r];
-                w = g[(size_t)(r / Nq) * Bv + j];
+            if (j < Bv && off >= 0) {
+                p = idx[(size_t)j * pitch + off];
+                w = g[(size_t)iq_s[rr] * Bv + j];
             }
             idx_s[jj][rr] = p;
             w_s[rr][jj] = w;
@@ -129,51 +155,202 @@ dq_gather_kernel(const T* __restrict__ v, const IdxT* __restrict__ idx, const fl
 }
 
 // ---------------------------------------------------------------------------------------
-// dv (baseline): one CTA = one image x one D-slice of 32*kDvWarps dims; fp32 accumulators for
-// every patch live in shared memory.  Each warp owns 32 dims (one per lane) of ALL patches and
-// streams ALL M rows, so no two threads ever touch the same accumulator: no atomics, and the
-// summation order (row order) is fixed => deterministic.
+// dv step 1: stable counting sort of one image's rows by winning patch.
+//   The Bq queries are cut into kSortGroups groups; warp (j,c) owns group c of image j.
+//   count  : per-(j,c) histogram of the winners            -> cnt[j][c][p]
+//   offsets: exclusive scan over (p major, c minor)        -> start[j][c][p], seg[j][p]
+//   scatter: rows in order, rank inside a 32-row chunk via __match_any_sync => stable
+//   entry = { row index into q, weight = row_scale[r] * g[i][j] }
 // ---------------------------------------------------------------------------------------
-constexpr int kDvWarps = 4;
+constexpr int kSortGroups = 8;
+constexpr int kSortWarps = 4;
 
-template <typename T, typename IdxT, typename OutT>
-__global__ void __launch_bounds__(kDvWarps * 32)
-dv_scatter_kernel(const T* __restrict__ q, const IdxT* __restrict__ idx, const float* __restrict__ g,
-                  const float* __restrict__ row_scale, const float* __restrict__ Tptr,
-                  int M, int Bv, int Nq, int Nv, int D, int DS, OutT* __restrict__ dv) {
-    extern __shared__ float acc_s[];                 // [Nv][DS]
-    const int nslice = D / DS;
-    const int j = blockIdx.x / nslice;
-    const int d0 = (blockIdx.x % nslice) * DS;
+struct __align__(8) DvEntry { uint32_t row; float w; };
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kSortWarps * 32)
+dv_count_kernel(const IdxT* __restrict__ idx, int j0, int nj, int Bq, int Nq, int Nv, int nq_pad,
+                uint32_t* __restrict__ cnt) {
+    extern __shared__ uint32_t sm_cnt[];                       // [kSortWarps][Nv]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float Tval = *Tptr;
+    const int item = blockIdx.x * kSortWarps + warp;           // (jl, c)
+    uint32_t* my = sm_cnt + warp * Nv;
+    for (int p = lane; p < Nv; p += 32) my[p] = 0;
+    __syncwarp();
+    if (item < nj * kSortGroups) {
+        const int jl = item / kSortGroups, c = item % kSortGroups;
+        const int qper = (Bq + kSortGroups - 1) / kSortGroups;
+        const int i0 = c * qper, i1 = min(Bq, i0 + qper);
+        const IdxT* base = idx + (size_t)(j0 + jl) * Bq * nq_pad;
+        for (int i = i0; i < i1; ++i)
+            for (int a = lane; a < Nq; a += 32) atomicAdd(&my[(int)base[(size_t)i * nq_pad + a]], 1u);
+        __syncwarp();
+        uint32_t* out = cnt + ((size_t)jl * kSortGroups + c) * Nv;
+        for (int p = lane; p < Nv; p += 32) out[p] = my[p];
+    }
+}
 
-    for (int t = threadIdx.x; t < Nv * DS; t += kDvWarps * 32) acc_s[t] = 0.f;
+// one thread per (jl, p): running offsets over the groups; then an in-block scan over p
+__global__ void __launch_bounds__(1024)
+dv_offsets_kernel(const uint32_t* __restrict__ cnt, int nj, int Nv, uint32_t* __restrict__ start,
+                  uint32_t* __restrict__ seg) {
+    // one block per image, Nv <= 65535 handled with a strided serial scan over 1024-wide tiles
+    __shared__ uint32_t tile[1024];
+    __shared__ uint32_t carry;
+    const int jl = blockIdx.x;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-
-    const IdxT* idxj = idx + (size_t)j * M;
-    const int dcol = warp * 32 + lane;               // this thread's column inside the slice
-    const bool active = dcol < DS;
-    for (int base = 0; base < M; base += 32) {
-        const int r = base + lane;
-        int p = 0; float w = 0.f;
-        if (r < M) {
-            p = (int)idxj[r];
-            w = Tval * row_scale[r] * g[(size_t)(r / Nq) * Bv + j];
+    for (int p0 = 0; p0 < Nv; p0 += 1024) {
+        const int p = p0 + threadIdx.x;
+        uint32_t tot = 0;
+        if (p < Nv)
+            for (int c = 0; c < kSortGroups; ++c) tot += cnt[((size_t)jl * kSortGroups + c) * Nv + p];
+        tile[threadIdx.x] = tot;
+        __syncthreads();
+        // Hillis-Steele inclusive scan
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t x = (threadIdx.x >= (unsigned)o) ? tile[threadIdx.x - o] : 0u;
+            __syncthreads();
+            tile[threadIdx.x] += x;
+            __syncthreads();
         }
-        const int nrow = min(32, M - base);
-        const T* src = q + (size_t)base * D + d0 + dcol;
-        for (int l = 0; l < nrow; ++l) {
-            const float wl = __shfl_sync(0xffffffffu, w, l);
-            const int pl = __shfl_sync(0xffffffffu, p, l);
-            if (wl != 0.f && active) acc_s[pl * DS + dcol] += wl * (float)src[(size_t)l * D];
+        const uint32_t excl = carry + tile[threadIdx.x] - tot;
+        if (p < Nv) {
+            seg[(size_t)jl * (Nv + 1) + p] = excl;
+            uint32_t run = excl;
+            for (int c = 0; c < kSortGroups; ++c) {
+                start[((size_t)jl * kSortGroups + c) * Nv + p] = run;
+                run += cnt[((size_t)jl * kSortGroups + c) * Nv + p];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += tile[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg[(size_t)jl * (Nv + 1) + Nv] = carry;
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kSortWarps * 32)
+dv_scatter_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g,
+                       const float* __restrict__ row_scale, const uint32_t* __restrict__ start,
+                       int j0, int nj, int Bq, int Bv, int Nq, int Nv, int nq_pad, size_t Mrows,
+                       DvEntry* __restrict__ entries) {
+    extern __shared__ uint32_t sm_cur[];                       // [kSortWarps][Nv]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kSortWarps + warp;
+    if (item >= nj * kSortGroups) return;
+    const int jl = item / kSortGroups, c = item % kSortGroups;
+    uint32_t* cur = sm_cur + warp * Nv;
+    const uint32_t* st = start + ((size_t)jl * kSortGroups + c) * Nv;
+    for (int p = lane; p < Nv; p += 32) cur[p] = st[p];
+    __syncwarp();
+    const int j = j0 + jl;
+    const int qper = (Bq + kSortGroups - 1) / kSortGroups;
+    const int i0 = c * qper, i1 = min(Bq, i0 + qper);
+    const IdxT* base = idx + (size_t)j * Bq * nq_pad;
+    DvEntry* out = entries + (size_t)jl * Mrows;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int i = i0; i < i1; ++i) {
+        const float gij = g[(size_t)i * Bv + j];
+        for (int a0 = 0; a0 < Nq; a0 += 32) {
+            const int a = a0 + lane;
+            const bool valid = a < Nq;
+            const int p = valid ? (int)base[(size_t)i * nq_pad + a] : -1 - lane;   // distinct dummies
+            const uint32_t peers = __match_any_sync(0xffffffffu, p);
+            uint32_t pos = 0;
+            if (valid) pos = cur[p] + __popc(peers & lt);
+            __syncwarp();
+            if (valid && (peers & lt) == 0u) cur[p] += __popc(peers);            // group leader advances the cursor
+            __syncwarp();
+            if (valid) {
+                const int r = i * Nq + a;
+                DvEntry e; e.row = (uint32_t)r; e.w = row_scale[r] * gij;
+                out[pos] = e;
+            }
         }
     }
-    __syncthreads();
-    OutT* out = dv + (size_t)j * Nv * D + d0;
-    for (int t = threadIdx.x; t < Nv * DS; t += kDvWarps * 32) {
-        const int p = t / DS, d = t % DS;
-        out[(size_t)p * D + d] = (OutT)acc_s[t];
+}
+
+// ---------------------------------------------------------------------------------------
+// dv step 2: one warp per (image, patch) segment; lanes own 16-byte chunks of D; the (row,
+// weight) list is read 32 entries at a time and broadcast with shuffles; 4 rows in flight.
+// ---------------------------------------------------------------------------------------
+template <typename T, typename OutT, int KCH>
+__global__ void __launch_bounds__(256)
+dv_gather_kernel(const T* __restrict__ q, const DvEntry* __restrict__ entries, const uint32_t* __restrict__ seg,
+                 const float* __restrict__ Tptr, int j0, int nj, int Nv, int D, size_t Mrows,
+                 OutT* __restrict__ dv) {
+    constexpr int E = Vec16<T>::kElems;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long sid = (long long)blockIdx.x * 8 + warp;
+    if (sid >= (long long)nj * Nv) return;
+    const int jl = (int)(sid / Nv), p = (int)(sid % Nv);
+    const uint32_t e0 = seg[(size_t)jl * (Nv + 1) + p], e1 = seg[(size_t)jl * (Nv + 1) + p + 1];
+    const DvEntry* list = entries + (size_t)jl * Mrows;
+    const int nchunk = D / E;
+
+    float acc[KCH][E];
+#pragma unroll
+    for (int b = 0; b < KCH; ++b)
+#pragma unroll
+        for (int c = 0; c < E; ++c) acc[b][c] = 0.f;
+
+    for (uint32_t base = e0; base < e1; base += 32) {
+        DvEntry mine; mine.row = 0; mine.w = 0.f;
+        if (base + lane < e1) mine = list[base + lane];
+        const int n = min(32u, e1 - base);
+        int l = 0;
+        for (; l + 4 <= n; l += 4) {
+            float f[4][KCH][E];
+            float w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t r = __shfl_sync(0xffffffffu, mine.row, l + u);
+                w[u] = __shfl_sync(0xffffffffu, mine.w, l + u);
+                const T* src = q + (size_t)r * D;
+#pragma unroll
+                for (int b = 0; b < KCH; ++b) {
+                    const int ch = lane + 32 * b;
+                    if (ch < nchunk) Vec16<T>::load(src + ch * E, f[u][b]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int b = 0; b < KCH; ++b)
+                    if (lane + 32 * b < nchunk) {
+#pragma unroll
+                        for (int c = 0; c < E; ++c) acc[b][c] = fmaf(w[u], f[u][b][c], acc[b][c]);
+                    }
+        }
+        for (; l < n; ++l) {
+            const uint32_t r = __shfl_sync(0xffffffffu, mine.row, l);
+            const float w = __shfl_sync(0xffffffffu, mine.w, l);
+            const T* src = q + (size_t)r * D;
+#pragma unroll
+            for (int b = 0; b < KCH; ++b) {
+                const int ch = lane + 32 * b;
+                if (ch < nchunk) {
+                    float f[E];
+                    Vec16<T>::load(src + ch * E, f);
+#pragma unroll
+                    for (int c = 0; c < E; ++c) acc[b][c] = fmaf(w, f[c], acc[b][c]);
+                }
+            }
+        }
+    }
+    const float Tval = *Tptr;
+    OutT* out = dv + ((size_t)(j0 + jl) * Nv + p) * D;
+#pragma unroll
+    for (int b = 0; b < KCH; ++b) {
+        const int ch = lane + 32 * b;
+        if (ch < nchunk) {
+            float f[E];
+#pragma unroll
+            for (int c = 0; c < E; ++c) f[c] = acc[b][c] * Tval;
+            StoreAs<OutT, E>::put(out + ch * E, f);
+        }
     }
 }
 
@@ -196,51 +373,85 @@ dT_kernel(const float* __restrict__ g, const float* __restrict__ clip, size_t n,
     }
 }
 
-static int pick_dv_slice(int Nv, int D) {
-    // largest slice (multiple of 8 dividing D) whose accumulators fit ~160 KB of shared memory
-    int best = 0;
-    for (int ds = 8; ds <= D && ds <= 32 * kDvWarps; ds += 8)
-        if (D % ds == 0 && (size_t)Nv * ds * 4 <= 160 * 1024) best = ds;
-    return best;
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct DvPlan {
+    int jb;                 // images sorted per batch (bounds the entry list to ~1 GiB)
+    size_t off_cnt, off_start, off_seg, off_entries, total;
+};
+static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv) {
+    DvPlan pl;
+    const size_t M = (size_t)Bq * Nq;
+    size_t jb = ((size_t)1 << 30) / (M * sizeof(DvEntry));
+    if (jb < 1) jb = 1;
+    if (jb > (size_t)Bv) jb = Bv;
+    pl.jb = (int)jb;
+    size_t o = 0;
+    pl.off_cnt = o;     o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
+    pl.off_start = o;   o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
+    pl.off_seg = o;     o += align_up(jb * ((size_t)Nv + 1) * 4, 256);
+    pl.off_entries = o; o += align_up(jb * M * sizeof(DvEntry), 256);
+    pl.total = o;
+    return pl;
 }
 
 template <typename T, typename IdxT>
 static int bwd_typed(const void* q, const void* v, const void* idx, const float* g,
                      const float* clip, const float* row_scale, const float* Tp,
                      int Bq, int Bv, int Nq, int Nv, int D,
-                     void* dq, void* dv, int dv_f32, float* dT, cudaStream_t st) {
+                     void* dq, void* dv, int dv_f32, float* dT, void* ws, cudaStream_t st) {
     const int M = Bq * Nq;
+    const int nq_pad = nq_padded(Nq);
     constexpr int E = Vec16<T>::kElems;
+    const int kch = ceil_div(D / E, 32);
+    if (kch < 1 || kch > 4) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
     if (dq) {
-        const int kch = ceil_div(D / E, 32);
         const int grid = ceil_div(M, kDqRows);
 #define TRIAD_DQ(K) dq_gather_kernel<T, IdxT, K><<<grid, 256, 0, st>>>( \
-        (const T*)v, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, (T*)dq)
+        (const T*)v, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, nq_pad, (T*)dq)
         switch (kch) {
             case 1: TRIAD_DQ(1); break;
             case 2: TRIAD_DQ(2); break;
             case 3: TRIAD_DQ(3); break;
-            case 4: TRIAD_DQ(4); break;
-            default: return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large for dq kernel");
+            default: TRIAD_DQ(4); break;
         }
 #undef TRIAD_DQ
         TRIAD_LAUNCH_CHECK("dq_gather_kernel");
     }
     if (dv) {
-        const int DS = pick_dv_slice(Nv, D);
-        if (DS == 0) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: Nv too large for dv kernel");
-        const size_t smem = (size_t)Nv * DS * 4;
-        const int grid = Bv * (D / DS);
-        if (dv_f32 || sizeof(T) == 4) {
-            auto kern = dv_scatter_kernel<T, IdxT, float>;
-            TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kDvWarps * 32, smem, st>>>((const T*)q, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, DS, (float*)dv);
-        } else {
-            auto kern = dv_scatter_kernel<T, IdxT, T>;
-            TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kDvWarps * 32, smem, st>>>((const T*)q, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, DS, (T*)dv);
+        const DvPlan pl = dv_plan(Bq, Bv, Nq, Nv);
+        uint32_t* cnt = (uint32_t*)((char*)ws + pl.off_cnt);
+        uint32_t* start = (uint32_t*)((char*)ws + pl.off_start);
+        uint32_t* seg = (uint32_t*)((char*)ws + pl.off_seg);
+        DvEntry* entries = (DvEntry*)((char*)ws + pl.off_entries);
+        const size_t smem = (size_t)kSortWarps * Nv * 4;
+        if (smem > 48 * 1024) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: Nv too large for the dv sort");
+        const bool out_f32 = dv_f32 || sizeof(T) == 4;
+        for (int j0 = 0; j0 < Bv; j0 += pl.jb) {
+            const int nj = (Bv - j0 < pl.jb) ? (Bv - j0) : pl.jb;
+            const int sort_grid = ceil_div(nj * kSortGroups, kSortWarps);
+            dv_count_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>((const IdxT*)idx, j0, nj, Bq, Nq, Nv, nq_pad, cnt);
+            TRIAD_LAUNCH_CHECK("dv_count_kernel");
+            dv_offsets_kernel<<<nj, 1024, 0, st>>>(cnt, nj, Nv, start, seg);
+            TRIAD_LAUNCH_CHECK("dv_offsets_kernel");
+            dv_scatter_sort_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(
+                (const IdxT*)idx, g, row_scale, start, j0, nj, Bq, Bv, Nq, Nv, nq_pad, (size_t)M, entries);
+            TRIAD_LAUNCH_CHECK("dv_scatter_sort_kernel");
+            const long long nseg = (long long)nj * Nv;
+            const unsigned ggrid = (unsigned)((nseg + 7) / 8);
+#define TRIAD_DV(OUT, K) dv_gather_kernel<T, OUT, K><<<ggrid, 256, 0, st>>>( \
+            (const T*)q, entries, seg, Tp, j0, nj, Nv, D, (size_t)M, (OUT*)dv)
+            if (out_f32) {
+                switch (kch) { case 1: TRIAD_DV(float, 1); break; case 2: TRIAD_DV(float, 2); break;
+                               case 3: TRIAD_DV(float, 3); break; default: TRIAD_DV(float, 4); break; }
+            } else {
+                switch (kch) { case 1: TRIAD_DV(T, 1); break; case 2: TRIAD_DV(T, 2); break;
+                               case 3: TRIAD_DV(T, 3); break; default: TRIAD_DV(T, 4); break; }
+            }
+#undef TRIAD_DV
+            TRIAD_LAUNCH_CHECK("dv_gather_kernel");
         }
-        TRIAD_LAUNCH_CHECK("dv_scatter_kernel");
     }
     if (dT) {
         dT_kernel<<<1, 1024, 0, st>>>(g, clip, (size_t)Bq * Bv, Tp, dT);
@@ -253,26 +464,31 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
 
 using namespace triad;
 
-extern "C" size_t triad_maxmean_bwd_workspace_bytes(int, int, int, int, int, int) { return 256; }
+extern "C" size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype) {
+    (void)D; (void)dtype;
+    if (Bq <= 0 || Bv <= 0 || Nq <= 0 || Nv <= 0) return 0;
+    return dv_plan(Bq, Bv, Nq, Nv).total;
+}
 
 extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
                                  const float* clip, const float* row_scale, const float* temperature,
                                  int Bq, int Bv, int Nq, int Nv, int D, int dtype,
                                  void* dq, void* dv, int dv_f32, float* dT,
                                  void* ws, size_t ws_bytes, void* stream) {
-    (void)ws; (void)ws_bytes;
     if (!q || !v || !idx || !g || !row_scale || !temperature) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: null pointer");
     if (dT && !clip) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: dT needs clip");
     if (Bq <= 0 || Bv <= 0 || Nq <= 0 || Nv <= 0 || D <= 0 || D % 8 != 0 || Nv > 65535)
         return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_bwd: bad shape");
     if (dtype != TRIAD_DTYPE_F32 && dtype != TRIAD_DTYPE_BF16) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: dtype");
-    if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)dq | (uintptr_t)dv) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_bwd: 16-byte alignment");
+    if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)dq | (uintptr_t)dv | (uintptr_t)ws) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_bwd: 16-byte alignment");
+    if (dv && (!ws || ws_bytes < triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype)))
+        return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const bool wide = Nv > 256;
     if (dtype == TRIAD_DTYPE_BF16) {
-        return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, st)
-                    : bwd_typed<__nv_bfloat16, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, st);
+        return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st)
+                    : bwd_typed<__nv_bfloat16, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st);
     }
-    return wide ? bwd_typed<float, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, st)
-                : bwd_typed<float, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, st);
+    return wide ? bwd_typed<float, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st)
+                : bwd_typed<float, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st);
 }

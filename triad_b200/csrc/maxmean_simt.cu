@@ -82,7 +82,7 @@ template <typename T, bool kBF16Round, typename IdxT>
 __global__ void __launch_bounds__(256)
 maxmean_simt_kernel(const T* __restrict__ q, const T* __restrict__ v,
                     const float* __restrict__ row_scale, const float* __restrict__ Tptr, int inv_T,
-                    int M, int Bv, int Nq, int Nv, int D, int G, int S,
+                    int M, int Bv, int Nq, int Nv, int D, int G, int S, int nq_pad,
                     float* __restrict__ part, IdxT* __restrict__ idx) {
     __shared__ float Qs[kSimtK][kSimtRows + 1];
     __shared__ __align__(16) float Vs[kSimtK][kSimtCols + 4];
@@ -159,7 +159,10 @@ maxmean_simt_kernel(const T* __restrict__ q, const T* __restrict__ v,
         float val = 0.f;
         if (r < M) {
             val = bv * row_scale[r];
-            if (idx != nullptr) idx[(size_t)j * M + r] = (IdxT)bi;
+            if (idx != nullptr) {
+                const int qi = r / Nq;
+                idx[((size_t)j * (M / Nq) + qi) * nq_pad + (r - qi * Nq)] = (IdxT)bi;
+            }
         }
         store_group_partials(part, j, g, G, S, row0, M, Nq, val, lane);
     }
@@ -174,10 +177,10 @@ static int launch_simt_t(const void* q, const void* v, const float* row_scale, c
     dim3 grid((unsigned)(pl.G * Bv));
     if (Nv <= 256)
         maxmean_simt_kernel<T, R, uint8_t><<<grid, 256, 0, st>>>(
-            (const T*)q, (const T*)v, row_scale, Tp, inv_T, M, Bv, Nq, Nv, D, pl.G, pl.S, part, (uint8_t*)idx);
+            (const T*)q, (const T*)v, row_scale, Tp, inv_T, M, Bv, Nq, Nv, D, pl.G, pl.S, nq_padded(Nq), part, (uint8_t*)idx);
     else
         maxmean_simt_kernel<T, R, uint16_t><<<grid, 256, 0, st>>>(
-            (const T*)q, (const T*)v, row_scale, Tp, inv_T, M, Bv, Nq, Nv, D, pl.G, pl.S, part, (uint16_t*)idx);
+            (const T*)q, (const T*)v, row_scale, Tp, inv_T, M, Bv, Nq, Nv, D, pl.G, pl.S, nq_padded(Nq), part, (uint16_t*)idx);
     TRIAD_LAUNCH_CHECK("maxmean_simt_kernel");
     return TRIAD_OK;
 }

@@ -34,7 +34,7 @@ class TokenSims:
         self.q, self.v, self.temperature = q, v, temperature
         self.row_scale, self.mask = scale, mask
         self.clip = clip_f32            # fp32 (Bq,Bv), attached to the autograd graph
-        self.idx_t = idx                # [Bv, Bq*Nq] uint8/uint16 (library layout)
+        self.idx_t = idx                # [Bv, Bq*nq_pad] uint8/uint16 (library layout)
         self.prefix = prefix
         self.shape = torch.Size((q.shape[0], v.shape[0], q.shape[1], v.shape[1]))
         self.dtype = q.dtype
@@ -42,8 +42,7 @@ class TokenSims:
 
     def argmax(self) -> torch.Tensor:
         """(Bq,Bv,Nq) int64 in the reference's layout: torch.max(token_sims, dim=3)[1]."""
-        Bq, Bv, Nq, _ = self.shape
-        return self.idx_t.view(Bv, Bq, Nq).permute(1, 0, 2).to(torch.int64).contiguous()
+        return ops.idx_to_reference_layout(self.idx_t, self.shape[0], self.shape[2])
 
     def materialize(self) -> torch.Tensor:
         """Dense token_sims exactly as the reference builds it (model.py:384-387).  Debug /
@@ -139,6 +138,10 @@ class TriadSimilarityMixin:
     def _similarities(self, q_feats, visual_feats, attention_mask, prefix):
         if q_feats.dim() != 3 or visual_feats.dim() != 3:
             raise ValueError("expected (B,N,D) embeddings")
+        ops._require_cuda(q_feats, visual_feats, attention_mask)
+        if q_feats.dtype != visual_feats.dtype or q_feats.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"triad_b200 supports float32 and bfloat16 embeddings of one dtype, got "
+                            f"{q_feats.dtype} / {visual_feats.dtype}")
         Bq, Nq, _ = q_feats.shape
         scale = ops.row_scale(attention_mask, Bq, Nq, q_feats.device)
         clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale,

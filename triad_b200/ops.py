@@ -80,9 +80,20 @@ def idx_dtype(Nv: int) -> torch.dtype:
     return torch.uint8 if Nv <= 256 else torch.uint16
 
 
+def nq_padded(Nq: int) -> int:
+    """Row pitch of one query inside the argmax index buffer ([Bv][Bq][nq_pad], see include/triad_b200.h)."""
+    return (Nq + 15) // 16 * 16
+
+
+def idx_to_reference_layout(idx: torch.Tensor, Bq: int, Nq: int) -> torch.Tensor:
+    """Library layout [Bv, Bq*nq_pad] -> the reference's torch.max(token_sims, dim=3)[1]: (Bq,Bv,Nq) int64."""
+    Bv = idx.shape[0]
+    return idx.view(Bv, Bq, nq_padded(Nq))[:, :, :Nq].permute(1, 0, 2).to(torch.int64).contiguous()
+
+
 def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.Tensor,
                 want_idx: bool = True, flags: int = 0, check_watchdog: bool = False):
-    """clip fp32 [Bq,Bv], idx [Bv, Bq*Nq] (uint8/uint16) or None."""
+    """clip fp32 [Bq,Bv], idx [Bv, Bq*nq_padded(Nq)] (uint8/uint16) or None."""
     lib = _lib.load()
     _require_cuda(q, v, scale, T)
     if q.dtype != v.dtype:
@@ -94,7 +105,7 @@ def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.
         raise ValueError("embedding dims differ")
     dt = _dtype_code(q)
     clip = torch.empty(Bq, Bv, dtype=torch.float32, device=q.device)
-    idx = torch.empty(Bv, Bq * Nq, dtype=idx_dtype(Nv), device=q.device) if want_idx else None
+    idx = torch.empty(Bv, Bq * nq_padded(Nq), dtype=idx_dtype(Nv), device=q.device) if want_idx else None
     nws = lib.triad_maxmean_fwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dt)
     ws = _Workspace.get(nws, q.device, "fwd")
     check(lib.triad_maxmean_fwd(q.data_ptr(), v.data_ptr(), scale.data_ptr(), T.data_ptr(),
