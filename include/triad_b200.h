@@ -117,12 +117,15 @@ int triad_infonce_finish(const float* clip_rows, int rows, int B, int row0,
  * g fp32 [Bq,Bv] is dLoss/dclip.  dq is written in `dtype` ([Bq,Nq,D]); dv is written as
  * fp32 [Bv,Nv,D] when dv_f32 != 0 (partial to be reduce-scattered across ranks) else in
  * `dtype`; dT fp32 [1].  Any of dq / dv / dT may be NULL to skip it. */
+#define TRIAD_BWD_DEFAULT      0
+#define TRIAD_BWD_GENERIC_DQ   1   /* L2-served gather kernel for dq (always used for fp32 / D % 64 != 0) */
+#define TRIAD_BWD_GENERIC_DV   2   /* per-segment L2-served gather for dv                                 */
 size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
 int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
                       const float* clip, const float* row_scale, const float* temperature,
                       int Bq, int Bv, int Nq, int Nv, int D, int dtype,
                       void* dq, void* dv, int dv_f32, float* dT,
-                      void* ws, size_t ws_bytes, void* stream);
+                      void* ws, size_t ws_bytes, int flags, void* stream);
 
 /* ---- retrieval: one query against a gallery, top-k ---------------------------------- */
 /* Replaces the per-pair aggregators retrieval.py:106-110 / :190-193 (direction 0:

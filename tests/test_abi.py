@@ -78,8 +78,8 @@ def test_argument_validation_without_gpu(lib):
     assert lib.triad_infonce_partial(one, 4, 4, 2, one, one, one, 1 << 20, null) == E["shape"]        # row0+rows > B
     assert lib.triad_infonce_finish(one, 4, 4, 0, one, one, 1, 1.0, one, one, one, 8, null) == E["ws"]
     b = lib.triad_maxmean_bwd
-    assert b(one, one, null, one, one, one, one, 2, 2, 4, 8, 64, 1, one, one, 0, one, one, 256, null) == E["arg"]
-    assert b(one, one, one, one, one, one, one, 2, 2, 4, 8, 63, 1, one, one, 0, one, one, 256, null) == E["shape"]
+    assert b(one, one, null, one, one, one, one, 2, 2, 4, 8, 64, 1, one, one, 0, one, one, 256, 0, null) == E["arg"]
+    assert b(one, one, one, one, one, one, one, 2, 2, 4, 8, 63, 1, one, one, 0, one, one, 256, 0, null) == E["shape"]
     assert lib.triad_topk(one, 10, 11, one, one, one, 1 << 20, null) == E["shape"]
     assert lib.triad_diag_ranks(null, 4, one, null) == E["arg"]
     assert lib.triad_similarity_matrix(one, one, one, 0, 1, 1, 8, one, null) == E["shape"]

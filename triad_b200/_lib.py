@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtriad_b200.so")
 OK = 0
 DTYPE_F32, DTYPE_BF16 = 0, 1
 FWD_DEFAULT, FWD_FORCE_SIMT, FWD_FORCE_1CTA, FWD_DIVIDE_BY_T = 0, 1, 2, 4
+BWD_DEFAULT, BWD_GENERIC_DQ, BWD_GENERIC_DV = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol of include/triad_b200.h
 SIGNATURES = {
@@ -36,7 +37,7 @@ SIGNATURES = {
     "triad_maxmean_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "triad_maxmean_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int, c_int,
-                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "triad_retrieve_workspace_bytes": (c_size_t, [c_int] * 5),
     "triad_retrieve_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                       c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -400,13 +400,16 @@ template <typename T, typename IdxT>
 static int bwd_typed(const void* q, const void* v, const void* idx, const float* g,
                      const float* clip, const float* row_scale, const float* Tp,
                      int Bq, int Bv, int Nq, int Nv, int D,
-                     void* dq, void* dv, int dv_f32, float* dT, void* ws, cudaStream_t st) {
+                     void* dq, void* dv, int dv_f32, float* dT, void* ws, int bwd_flags, cudaStream_t st) {
     const int M = Bq * Nq;
     const int nq_pad = nq_padded(Nq);
     constexpr int E = Vec16<T>::kElems;
     const int kch = ceil_div(D / E, 32);
     if (kch < 1 || kch > 4) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
-    if (dq) {
+    if (dq && sizeof(T) == 2 && dq_tile_supported(D, TRIAD_DTYPE_BF16) && !(bwd_flags & TRIAD_BWD_GENERIC_DQ)) {
+        const int rc = launch_dq_tile(v, idx, (int)sizeof(IdxT), g, row_scale, Tp, M, Bv, Nq, Nv, D, dq, st);
+        if (rc) return rc;
+    } else if (dq) {
         const int grid = ceil_div(M, kDqRows);
 #define TRIAD_DQ(K) dq_gather_kernel<T, IdxT, K><<<grid, 256, 0, st>>>( \
         (const T*)v, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, nq_pad, (T*)dq)
@@ -474,7 +477,7 @@ extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, 
                                  const float* clip, const float* row_scale, const float* temperature,
                                  int Bq, int Bv, int Nq, int Nv, int D, int dtype,
                                  void* dq, void* dv, int dv_f32, float* dT,
-                                 void* ws, size_t ws_bytes, void* stream) {
+                                 void* ws, size_t ws_bytes, int flags, void* stream) {
     if (!q || !v || !idx || !g || !row_scale || !temperature) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: null pointer");
     if (dT && !clip) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: dT needs clip");
     if (Bq <= 0 || Bv <= 0 || Nq <= 0 || Nv <= 0 || D <= 0 || D % 8 != 0 || Nv > 65535)
@@ -486,9 +489,9 @@ extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, 
     cudaStream_t st = (cudaStream_t)stream;
     const bool wide = Nv > 256;
     if (dtype == TRIAD_DTYPE_BF16) {
-        return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st)
-                    : bwd_typed<__nv_bfloat16, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st);
+        return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st)
+                    : bwd_typed<__nv_bfloat16, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st);
     }
-    return wide ? bwd_typed<float, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st)
-                : bwd_typed<float, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, st);
+    return wide ? bwd_typed<float, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st)
+                : bwd_typed<float, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st);
 }

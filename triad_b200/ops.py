@@ -116,7 +116,8 @@ def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.
     return clip, idx
 
 
-def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_dT=True, dv_f32=False):
+def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_dT=True, dv_f32=False,
+                flags: int = 0):
     lib = _lib.load()
     q, v, g = q.contiguous(), v.contiguous(), g.contiguous()
     if g.dtype != torch.float32:
@@ -133,7 +134,7 @@ def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_d
     check(lib.triad_maxmean_bwd(q.data_ptr(), v.data_ptr(), idx.data_ptr(), g.data_ptr(), _ptr(clip),
                                 scale.data_ptr(), T.data_ptr(), Bq, Bv, Nq, Nv, D, dt,
                                 _ptr(dq), _ptr(dv), 1 if dv_f32 else 0, _ptr(dT),
-                                ws.data_ptr(), ws.numel(), _stream()), "triad_maxmean_bwd")
+                                ws.data_ptr(), ws.numel(), int(flags), _stream()), "triad_maxmean_bwd")
     return dq, dv, dT
 
 
