@@ -60,7 +60,9 @@ def main():
         return ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=dq, need_dv=dv, need_dT=False, flags=flags)
 
     outs = {}
-    for name, dq_, dv_, fl in (("dq tiled", True, False, 0), ("dq generic", True, False, _lib.BWD_GENERIC_DQ),
+    for name, dq_, dv_, fl in (("dq tiled", True, False, 0), ("dq tiled L1", True, False, _lib.BWD_DQ_L1),
+                               ("dq tiled L1 nopf", True, False, _lib.BWD_DQ_L1 | _lib.BWD_NO_PREFETCH),
+                               ("dq generic", True, False, _lib.BWD_GENERIC_DQ),
                                ("dv default", False, True, 0), ("dv generic", False, True, _lib.BWD_GENERIC_DV)):
         t = timeit(lambda: bwd(dq_, dv_, fl), iters)
         o = bwd(dq_, dv_, fl)

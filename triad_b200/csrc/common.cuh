@@ -58,10 +58,13 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
                       float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st);
 int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
 bool tc_supported(int Nv, int D);
-// tiled (L1-resident gather) dQ of the backward, bf16 only — bwd_dq_tile.cu
+// tiled dQ of the backward, bf16 only — bwd_dq_tile.cu (TMA/shared-memory gather, and the L1-resident variant)
+bool dq_smem_supported(int Nv, int D, int dtype);
+int launch_dq_smem(const void* v, const void* idx, const float* g, const float* row_scale, const float* Tp,
+                   int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, cudaStream_t st);
 bool dq_tile_supported(int D, int dtype);
 int launch_dq_tile(const void* v, const void* idx, int idx_bytes, const float* g, const float* row_scale,
-                   const float* Tp, int M, int Bv, int Nq, int Nv, int D, void* dq, cudaStream_t st);
+                   const float* Tp, int M, int Bv, int Nq, int Nv, int D, int prefetch, void* dq, cudaStream_t st);
 
 // ---- device helpers -----------------------------------------------------------------------
 #if defined(__CUDACC__)

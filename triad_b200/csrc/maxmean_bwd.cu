@@ -387,7 +387,7 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv) {
     if (jb < 1) jb = 1;
     if (jb > (size_t)Bv) jb = Bv;
     pl.jb = (int)jb;
-    size_t o = 0;
+    size_t o = 256;                                       // [0,256): control block (watchdog flag)
     pl.off_cnt = o;     o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_start = o;   o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_seg = o;     o += align_up(jb * ((size_t)Nv + 1) * 4, 256);
@@ -406,8 +406,13 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
     constexpr int E = Vec16<T>::kElems;
     const int kch = ceil_div(D / E, 32);
     if (kch < 1 || kch > 4) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
-    if (dq && sizeof(T) == 2 && dq_tile_supported(D, TRIAD_DTYPE_BF16) && !(bwd_flags & TRIAD_BWD_GENERIC_DQ)) {
-        const int rc = launch_dq_tile(v, idx, (int)sizeof(IdxT), g, row_scale, Tp, M, Bv, Nq, Nv, D, dq, st);
+    if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_smem_supported(Nv, D, TRIAD_DTYPE_BF16) &&
+        !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1))) {
+        const int rc = launch_dq_smem(v, idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, dq, (int*)ws, st);
+        if (rc) return rc;
+    } else if (dq && sizeof(T) == 2 && dq_tile_supported(D, TRIAD_DTYPE_BF16) && !(bwd_flags & TRIAD_BWD_GENERIC_DQ)) {
+        const int rc = launch_dq_tile(v, idx, (int)sizeof(IdxT), g, row_scale, Tp, M, Bv, Nq, Nv, D,
+                                      (bwd_flags & TRIAD_BWD_NO_PREFETCH) ? 0 : 1, dq, st);
         if (rc) return rc;
     } else if (dq) {
         const int grid = ceil_div(M, kDqRows);
@@ -484,9 +489,10 @@ extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, 
         return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_bwd: bad shape");
     if (dtype != TRIAD_DTYPE_F32 && dtype != TRIAD_DTYPE_BF16) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: dtype");
     if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)dq | (uintptr_t)dv | (uintptr_t)ws) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_bwd: 16-byte alignment");
-    if (dv && (!ws || ws_bytes < triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype)))
+    if (!ws || ws_bytes < (dv ? triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) : (size_t)256))
         return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    TRIAD_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, st));
     const bool wide = Nv > 256;
     if (dtype == TRIAD_DTYPE_BF16) {
         return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st)

@@ -311,20 +311,30 @@ static PFN_tmapEncodeTiled get_encode_fn() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                      const cuuint32_t* box) {
-    PFN_tmapEncodeTiled fn = get_encode_fn();
+}  // namespace tc
+
+// bf16 tiled tensor map, rank 2 or 3; swizzle128 selects SWIZZLE_128B (UMMA operands) or none (plain row tiles)
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box, bool swizzle128) {
+    tc::PFN_tmapEncodeTiled fn = tc::get_encode_fn();
     if (!fn) return fail_msg(TRIAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[96];
         snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
         return fail_msg(TRIAD_ERR_CUDA, buf);
     }
     return TRIAD_OK;
+}
+
+namespace tc {
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+    return encode_tmap_bf16(map, base, rank, dims, strides, box, true);
 }
 
 template <int kCtaGroup>

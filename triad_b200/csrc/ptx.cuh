@@ -6,6 +6,11 @@
 #include <stdint.h>
 
 namespace triad {
+
+// host: bf16 tiled tensor map (defined in maxmean_tc.cu)
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box, bool swizzle128);
+
 namespace ptx {
 
 constexpr unsigned long long kWatchdogNs = 4000000000ull;
@@ -40,7 +45,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Wait with a deadlock guard: if the barrier does not flip within kWatchdogNs the kernel raises the
 // global abort flag and every role drains out, so a pipeline bug costs an error code, not a hung GPU.
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
     const unsigned long long t0 = globaltimer();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
