@@ -54,6 +54,21 @@ __device__ __forceinline__ void fma8(float (&a)[8], float w, const uint4& u) {
 
 constexpr int kStages = 3;      // staging ring: group G computes, G+1 is the prefetch target, G+2 is being loaded
 
+// Two fp32 FMAs per issue slot (Blackwell FFMA2): acc (lo,hi) += w * (bf16 pair of one 32-bit word).
+// These kernels are issue-bound, so halving the FMA instruction count is a direct win.
+__device__ __forceinline__ void ffma2(float2& acc, float w, uint32_t pair) {
+    float2 wv = make_float2(w, w);
+    float2 vv = make_float2(__uint_as_float(pair << 16), __uint_as_float(pair & 0xffff0000u));
+    unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
+    const unsigned long long b = *reinterpret_cast<unsigned long long*>(&wv);
+    const unsigned long long c = *reinterpret_cast<unsigned long long*>(&vv);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(b), "l"(c));
+    acc = *reinterpret_cast<float2*>(&a);
+}
+__device__ __forceinline__ void fma8p(float2 (&a)[4], float w, const uint4& u) {
+    ffma2(a[0], w, u.x); ffma2(a[1], w, u.y); ffma2(a[2], w, u.z); ffma2(a[3], w, u.w);
+}
+
 template <typename IdxT> constexpr size_t smem_bytes() { return (size_t)kStages * kJG * kRows * (sizeof(IdxT) + sizeof(float)); }
 
 // kPF = prefetch distance in images (0 = none): before the rows of image j are gathered, every
@@ -199,13 +214,13 @@ using namespace ptx;
 constexpr int kRows = 512;
 constexpr int kThreads = 512;
 constexpr int kSlice = 64;
-constexpr int kJG = 4;           // images per idx/weight staging group
-constexpr int kStages = 3;       // idx/weight staging ring
+constexpr int kJG = 8;           // images per idx/weight staging group (one __syncthreads per group)
+constexpr int kStages = 2;       // idx/weight staging: double buffered
 constexpr int kVS = 5;           // V-slice ring depth (4 images of look-ahead)
 constexpr int kMaxNv = 256;
 constexpr uint32_t kVStageBytes = kMaxNv * kSlice * 2;                                   // 32 KB
-constexpr uint32_t kWBytes = kStages * kJG * kRows * 4;
-constexpr uint32_t kIdxBytes = kStages * kJG * kRows;
+constexpr uint32_t kWBytes = kStages * kJG * kRows * 4;      // weights g[i(r), j]
+constexpr uint32_t kIdxBytes = kStages * kJG * kRows * 4;    // winners as byte offsets p*128 into the V stage
 constexpr uint32_t kSmemBytes = kVS * kVStageBytes + kWBytes + kIdxBytes + 2 * 8 * kVS + 128;  // + alignment slack
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -218,7 +233,7 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     unsigned char* base = dq3_smem + (sbase - s0);
     unsigned char* v_s = base;
     float (*w_s)[kJG][kRows] = reinterpret_cast<float (*)[kJG][kRows]>(base + kVS * kVStageBytes);
-    uint8_t (*idx_s)[kJG][kRows] = reinterpret_cast<uint8_t (*)[kJG][kRows]>(base + kVS * kVStageBytes + kWBytes);
+    uint32_t (*off_s)[kJG][kRows] = reinterpret_cast<uint32_t (*)[kJG][kRows]>(base + kVS * kVStageBytes + kWBytes);
     const uint32_t bar_full = sbase + kVS * kVStageBytes + kWBytes + kIdxBytes;
     const uint32_t bar_empty = bar_full + 8 * kVS;
 
@@ -226,7 +241,9 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     const int slice = blockIdx.x;
     const int row0 = blockIdx.y * kRows;
 
-    // ---- staging role: thread t = tile row t -------------------------------------------------
+    // ---- staging role: thread t = tile row t.  A warp stages exactly the 32 rows it later gathers
+    //      for, so the staging buffers are warp-private: __syncwarp is all the ordering they need and
+    //      the warps of a CTA only meet at the V ring's mbarriers (they may drift up to kVS-1 images).
     const int rs = row0 + t;
     const bool rs_valid = rs < M;
     const int qi = rs_valid ? rs / Nq : 0;
@@ -238,18 +255,20 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     const int warp = t >> 5, lane = t & 31, grp = lane >> 3, c = lane & 7;
     const int rb = warp * 32 + grp * 8;
 
-    float acc[8][8];
+    float2 acc[8][4];                             // 8 rows x 4 packed (lo,hi) fp32 pairs
 #pragma unroll
     for (int k = 0; k < 8; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+        for (int e = 0; e < 4; ++e) acc[k][e] = make_float2(0.f, 0.f);
 
-    auto stage = [&](int j0, int st) {
-        uint8_t pi[kJG];
-        float pw[kJG];
+    // staging is split in two so the global loads of group G+1 are in flight while group G computes
+    uint8_t pi[kJG];
+    float pw[kJG];
+    auto stage_load = [&](int j0) {
         if (rs_valid && g_vec && j0 + kJG <= Bv) {
             const float4 a = __ldg(reinterpret_cast<const float4*>(g_row + j0));
-            pw[0] = a.x; pw[1] = a.y; pw[2] = a.z; pw[3] = a.w;
+            const float4 b = __ldg(reinterpret_cast<const float4*>(g_row + j0 + 4));
+            pw[0] = a.x; pw[1] = a.y; pw[2] = a.z; pw[3] = a.w; pw[4] = b.x; pw[5] = b.y; pw[6] = b.z; pw[7] = b.w;
 #pragma unroll
             for (int jj = 0; jj < kJG; ++jj) pi[jj] = __ldcs(idx_row + (size_t)(j0 + jj) * pitch);
         } else {
@@ -261,8 +280,10 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
                 pw[jj] = ok ? __ldg(g_row + j) : 0.f;
             }
         }
+    };
+    auto stage_store = [&](int st) {
 #pragma unroll
-        for (int jj = 0; jj < kJG; ++jj) { idx_s[st][jj][t] = pi[jj]; w_s[st][jj][t] = pw[jj]; }
+        for (int jj = 0; jj < kJG; ++jj) { off_s[st][jj][t] = (uint32_t)pi[jj] * (kSlice * 2); w_s[st][jj][t] = pw[jj]; }
     };
 
     const uint32_t stage_tx = (uint32_t)Nv * (kSlice * 2);
@@ -271,9 +292,9 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
         for (int s = 0; s < kVS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, kThreads / 32); }
         fence_barrier_init();
     }
-    stage(0, 0);
-    if (kJG < Bv) stage(kJG, 1);
-    __syncthreads();
+    stage_load(0);
+    stage_store(0);
+    __syncthreads();                 // barrier init visible to all warps (the only CTA-wide barrier)
     if (t == 0) {
         for (int jn = 0; jn < kVS - 1 && jn < Bv; ++jn) {
             mbar_expect_tx(bar_full + 8 * jn, stage_tx);
@@ -286,8 +307,8 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     bool ok = true;
     for (int j0 = 0; j0 < Bv; j0 += kJG) {
         const int jn = min(kJG, Bv - j0);
-        const int st1 = (st + 1 == kStages) ? 0 : st + 1;
-        const int st2 = (st1 + 1 == kStages) ? 0 : st1 + 1;
+        const bool more = j0 + kJG < Bv;
+        if (more) stage_load(j0 + kJG);
 #pragma unroll
         for (int jj = 0; jj < kJG; ++jj) {
             if (jj < jn) {
@@ -295,19 +316,18 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
                 if (ok) ok = mbar_wait(bar_full + 8 * vslot, vphase, abort_flag, 11);
                 ok = __all_sync(0xffffffffu, ok);
                 if (ok) {
-                    const uint2 pk = *reinterpret_cast<const uint2*>(&idx_s[st][jj][rb]);
+                    const uint4 oa = *reinterpret_cast<const uint4*>(&off_s[st][jj][rb]);
+                    const uint4 ob = *reinterpret_cast<const uint4*>(&off_s[st][jj][rb + 4]);
+                    const uint32_t off[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
                     const float4 wa = *reinterpret_cast<const float4*>(&w_s[st][jj][rb]);
                     const float4 wb = *reinterpret_cast<const float4*>(&w_s[st][jj][rb + 4]);
                     const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
                     const unsigned char* vs = v_s + vslot * kVStageBytes + c * 16;
                     uint4 d[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t p = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xffu;
-                        d[k] = *reinterpret_cast<const uint4*>(vs + p * (kSlice * 2));
-                    }
+                    for (int k = 0; k < 8; ++k) d[k] = *reinterpret_cast<const uint4*>(vs + off[k]);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) dq2::fma8(acc[k], w[k], d[k]);
+                    for (int k = 0; k < 8; ++k) dq2::fma8p(acc[k], w[k], d[k]);
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(bar_empty + 8 * vslot);
                     if (t == 0) {
@@ -326,9 +346,9 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
                 if (++vslot == kVS) { vslot = 0; vphase ^= 1; }
             }
         }
-        if (j0 + 2 * kJG < Bv) stage(j0 + 2 * kJG, st2);
-        __syncthreads();
-        st = st1;
+        if (more) stage_store(st ^ 1);
+        __syncwarp();
+        st ^= 1;
     }
 
     const float Tval = *Tptr;
@@ -341,7 +361,8 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
             uint32_t* w32 = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(acc[k][2 * e] * s, acc[k][2 * e + 1] * s);
+                const float2 f = acc[k][e];
+                __nv_bfloat162 h = __floats2bfloat162_rn(f.x * s, f.y * s);
                 w32[e] = *reinterpret_cast<uint32_t*>(&h);
             }
             *reinterpret_cast<uint4*>(dq + (size_t)r * D + slice * kSlice + c * 8) = o;
