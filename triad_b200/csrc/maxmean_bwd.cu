@@ -273,84 +273,66 @@ dv_scatter_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g
 }
 
 // ---------------------------------------------------------------------------------------
-// dv step 2: one warp per (image, patch) segment; lanes own 16-byte chunks of D; the (row,
-// weight) list is read 32 entries at a time and broadcast with shuffles; 4 rows in flight.
+// dv step 2: one warp per (image, patch) segment and 32-chunk column block of D (a 512-byte
+// bf16 column block per warp: D = 512 -> 2 warps per segment); lanes own 16-byte chunks; the
+// (row, weight) list is read 32 entries at a time (the next 32 prefetched) and broadcast with
+// shuffles; kU rows in flight per warp.  The pass is L2-latency bound, so it is shaped for
+// bytes in flight: few registers per thread (many resident warps) x kU independent loads each.
 // ---------------------------------------------------------------------------------------
-template <typename T, typename OutT, int KCH>
+constexpr int kDvU = 8;
+
+template <typename T, typename OutT>
 __global__ void __launch_bounds__(256)
 dv_gather_kernel(const T* __restrict__ q, const DvEntry* __restrict__ entries, const uint32_t* __restrict__ seg,
-                 const float* __restrict__ Tptr, int j0, int nj, int Nv, int D, size_t Mrows,
+                 const float* __restrict__ Tptr, int j0, int nj, int Nv, int D, int wps, size_t Mrows,
                  OutT* __restrict__ dv) {
     constexpr int E = Vec16<T>::kElems;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long sid = (long long)blockIdx.x * 8 + warp;
+    const long long wid = (long long)blockIdx.x * 8 + warp;
+    const long long sid = wid / wps;
+    const int ch = (int)(wid - sid * wps) * 32 + lane;          // this lane's 16-byte chunk of the row
     if (sid >= (long long)nj * Nv) return;
+    const bool act = ch * E < D;
     const int jl = (int)(sid / Nv), p = (int)(sid % Nv);
     const uint32_t e0 = seg[(size_t)jl * (Nv + 1) + p], e1 = seg[(size_t)jl * (Nv + 1) + p + 1];
     const DvEntry* list = entries + (size_t)jl * Mrows;
-    const int nchunk = D / E;
+    const T* qc = q + (act ? ch * E : 0);
 
-    float acc[KCH][E];
+    float acc[E];
 #pragma unroll
-    for (int b = 0; b < KCH; ++b)
-#pragma unroll
-        for (int c = 0; c < E; ++c) acc[b][c] = 0.f;
+    for (int c = 0; c < E; ++c) acc[c] = 0.f;
 
+    DvEntry next; next.row = 0; next.w = 0.f;
+    if (e0 + lane < e1) next = list[e0 + lane];
     for (uint32_t base = e0; base < e1; base += 32) {
-        DvEntry mine; mine.row = 0; mine.w = 0.f;
-        if (base + lane < e1) mine = list[base + lane];
+        const DvEntry mine = next;
+        next.row = 0; next.w = 0.f;
+        if (base + 32 + lane < e1) next = list[base + 32 + lane];
         const int n = min(32u, e1 - base);
-        int l = 0;
-        for (; l + 4 <= n; l += 4) {
-            float f[4][KCH][E];
-            float w[4];
+        for (int l = 0; l < n; l += kDvU) {
+            float f[kDvU][E];
+            float w[kDvU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t r = __shfl_sync(0xffffffffu, mine.row, l + u);
-                w[u] = __shfl_sync(0xffffffffu, mine.w, l + u);
-                const T* src = q + (size_t)r * D;
-#pragma unroll
-                for (int b = 0; b < KCH; ++b) {
-                    const int ch = lane + 32 * b;
-                    if (ch < nchunk) Vec16<T>::load(src + ch * E, f[u][b]);
-                }
+            for (int u = 0; u < kDvU; ++u) {
+                // slots past n re-read the segment's last entry with weight 0: no branch in the batch
+                const int src = min(l + u, n - 1);
+                const uint32_t r = __shfl_sync(0xffffffffu, mine.row, src);
+                const float ww = __shfl_sync(0xffffffffu, mine.w, src);
+                w[u] = (l + u < n) ? ww : 0.f;
+                Vec16<T>::load(qc + (size_t)r * D, f[u]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < kDvU; ++u)
 #pragma unroll
-                for (int b = 0; b < KCH; ++b)
-                    if (lane + 32 * b < nchunk) {
-#pragma unroll
-                        for (int c = 0; c < E; ++c) acc[b][c] = fmaf(w[u], f[u][b][c], acc[b][c]);
-                    }
-        }
-        for (; l < n; ++l) {
-            const uint32_t r = __shfl_sync(0xffffffffu, mine.row, l);
-            const float w = __shfl_sync(0xffffffffu, mine.w, l);
-            const T* src = q + (size_t)r * D;
-#pragma unroll
-            for (int b = 0; b < KCH; ++b) {
-                const int ch = lane + 32 * b;
-                if (ch < nchunk) {
-                    float f[E];
-                    Vec16<T>::load(src + ch * E, f);
-#pragma unroll
-                    for (int c = 0; c < E; ++c) acc[b][c] = fmaf(w, f[c], acc[b][c]);
-                }
-            }
+                for (int c = 0; c < E; ++c) acc[c] = fmaf(w[u], f[u][c], acc[c]);
         }
     }
-    const float Tval = *Tptr;
-    OutT* out = dv + ((size_t)(j0 + jl) * Nv + p) * D;
+    if (act) {
+        const float Tval = *Tptr;
+        float o[E];
 #pragma unroll
-    for (int b = 0; b < KCH; ++b) {
-        const int ch = lane + 32 * b;
-        if (ch < nchunk) {
-            float f[E];
-#pragma unroll
-            for (int c = 0; c < E; ++c) f[c] = acc[b][c] * Tval;
-            StoreAs<OutT, E>::put(out + ch * E, f);
-        }
+        for (int c = 0; c < E; ++c) o[c] = acc[c] * Tval;
+        StoreAs<OutT, E>::put(dv + ((size_t)(j0 + jl) * Nv + p) * D + ch * E, o);
     }
 }
 
@@ -405,7 +387,7 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
     const int nq_pad = nq_padded(Nq);
     constexpr int E = Vec16<T>::kElems;
     const int kch = ceil_div(D / E, 32);
-    if (kch < 1 || kch > 4) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
+    if (dq && (kch < 1 || kch > 4)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
     if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_smem_supported(Nv, D, TRIAD_DTYPE_BF16) &&
         !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1))) {
         const int rc = launch_dq_smem(v, idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, dq, (int*)ws, st);
@@ -446,18 +428,13 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
             dv_scatter_sort_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(
                 (const IdxT*)idx, g, row_scale, start, j0, nj, Bq, Bv, Nq, Nv, nq_pad, (size_t)M, entries);
             TRIAD_LAUNCH_CHECK("dv_scatter_sort_kernel");
-            const long long nseg = (long long)nj * Nv;
-            const unsigned ggrid = (unsigned)((nseg + 7) / 8);
-#define TRIAD_DV(OUT, K) dv_gather_kernel<T, OUT, K><<<ggrid, 256, 0, st>>>( \
-            (const T*)q, entries, seg, Tp, j0, nj, Nv, D, (size_t)M, (OUT*)dv)
-            if (out_f32) {
-                switch (kch) { case 1: TRIAD_DV(float, 1); break; case 2: TRIAD_DV(float, 2); break;
-                               case 3: TRIAD_DV(float, 3); break; default: TRIAD_DV(float, 4); break; }
-            } else {
-                switch (kch) { case 1: TRIAD_DV(T, 1); break; case 2: TRIAD_DV(T, 2); break;
-                               case 3: TRIAD_DV(T, 3); break; default: TRIAD_DV(T, 4); break; }
-            }
-#undef TRIAD_DV
+            const int wps = ceil_div(D / E, 32);                                   // warps per segment
+            const long long nwarps = (long long)nj * Nv * wps;
+            const unsigned ggrid = (unsigned)((nwarps + 7) / 8);
+            if (out_f32)
+                dv_gather_kernel<T, float><<<ggrid, 256, 0, st>>>((const T*)q, entries, seg, Tp, j0, nj, Nv, D, wps, (size_t)M, (float*)dv);
+            else
+                dv_gather_kernel<T, T><<<ggrid, 256, 0, st>>>((const T*)q, entries, seg, Tp, j0, nj, Nv, D, wps, (size_t)M, (T*)dv);
             TRIAD_LAUNCH_CHECK("dv_gather_kernel");
         }
     }
