@@ -275,21 +275,57 @@ def run_triad(args, cfg_key):
     value = float(B) * B / (ms * 1e-3)
 
     # ---- end-to-end arm: pinned host inputs -> H2D -> step -> loss D2H --------------------------
+    # Every step's embeddings start in PINNED HOST memory and its loss is read back on the host.  As in any
+    # input pipeline, the H2D copy of step i+1 is issued on a copy stream while step i computes (double
+    # buffered device staging); each step still pays for its own copy and its own D2H read inside the timed
+    # region, but copy and compute overlap instead of serialising.
     host = [(q.detach().cpu().pin_memory(), v.detach().cpu().pin_memory(),
              None if m is None else m.cpu().pin_memory()) for (q, v, m) in sets]
     d2h = {"bytes": 0}
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def issue_copy(i):
+        hq, hv, hm = host[i % n_sets]
+        with torch.cuda.stream(copy_stream):
+            q = hq.to(dev, non_blocking=True)
+            v = hv.to(dev, non_blocking=True)
+            m = None if hm is None else hm.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[i] = (q, v, m, ev)
 
     def e2e_step(i):
-        hq, hv, hm = host[i % n_sets]
-        q = hq.to(dev, non_blocking=True).requires_grad_(world == 1)
-        v = hv.to(dev, non_blocking=True).requires_grad_(world == 1)
-        m = None if hm is None else hm.to(dev, non_blocking=True)
+        if i not in staged:
+            issue_copy(i)
+        q, v, m, ev = staged.pop(i)
+        torch.cuda.current_stream().wait_event(ev)
+        for t in (q, v, m):
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream())
+        issue_copy(i + 1)                     # next step's inputs travel while this step computes
+        q.requires_grad_(world == 1); v.requires_grad_(world == 1)
         loss = step(q, v, m)
         d2h["bytes"] = 4
         return loss.item()                    # D2H read of the step's result
-    for i in range(min(args.warmup, 3)):
-        e2e_step(i)
-    e2e_ms = timed(e2e_step, args.steps)
+
+    def e2e_run(K):
+        staged.clear()
+        for i in range(K):
+            e2e_step(i)
+        staged.clear()                        # the look-ahead copy issued by the last step is not used
+
+    e2e_run(min(args.warmup, 3))
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    sync_all()
+    e2e_t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = e2e_t.item()
     h2d = in_bytes + (host[0][2].numel() * 8 if host[0][2] is not None else 0)
 
     # ---- roofline of the dominant kernel (tcgen05 forward) ---------------------------------------

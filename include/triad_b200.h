@@ -121,6 +121,7 @@ int triad_infonce_finish(const float* clip_rows, int rows, int B, int row0,
 #define TRIAD_BWD_GENERIC_DQ   1   /* L2-served gather kernel for dq (always used for fp32 / D % 64 != 0) */
 #define TRIAD_BWD_GENERIC_DV   2   /* per-segment L2-served gather for dv                                 */
 #define TRIAD_BWD_DQ_L1        8   /* tiled dq gathering through L1 instead of the TMA/shared-memory ring  */
+#define TRIAD_BWD_SMALL_BLOCKS 16   /* dv: 64 KB query blocks instead of 64 MB (test aid: multi-block path) */
 #define TRIAD_BWD_NO_PREFETCH  4   /* tiled dq without the prefetch.global.L1 look-ahead (A/B timing)      */
 size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
 int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,

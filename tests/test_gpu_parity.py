@@ -199,6 +199,41 @@ def test_full_size_properties_cfg2():
     assert abs(dT.item() - ((g64 * clip.double()).sum() / 1.5).item()) < 1e-5 * ssum
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_backward_variants_agree(masked):
+    """Every backward kernel variant (TMA/shared-memory dq, L1-resident dq, generic L2 dq; single-block and
+    multi-block dv, fp32-partial and bf16 dv) against the oracle's closed form and against each other."""
+    from triad_b200 import _lib, ops
+    B, Nq, Nv, D = 20, 77, 200, 256
+    q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=41, masked=masked, min_len=3)
+    ref = O.contrastive_step_closed_form(q, v, 1.5, mask)
+    qd, vd = q.cuda(), v.cuda()
+    scale = ops.row_scale(None if mask is None else mask.cuda(), B, Nq, qd.device)
+    Tt = torch.tensor(1.5, device=qd.device)
+    clip, idx = ops.maxmean_fwd(qd, vd, scale, Tt)
+    g = ref["g"].float().cuda()
+    # closed-form gradients for the winners the GPU actually chose (a near-tie flip, see
+    # _near_tie_report, would otherwise dominate the fp32 comparison)
+    idx_ref_layout = ops.idx_to_reference_layout(idx, B, Nq).cpu()
+    rdq, rdv, _ = O.maxmean_backward(q, v, idx_ref_layout, g.cpu(), 1.5, ref["row_scale"], clip.cpu())
+    ref = {"dq": rdq, "dv": rdv}
+    outs = {}
+    for name, flags, f32 in (("default", 0, False), ("dq_l1", _lib.BWD_DQ_L1, False),
+                             ("dq_l1_nopf", _lib.BWD_DQ_L1 | _lib.BWD_NO_PREFETCH, False),
+                             ("dq_generic", _lib.BWD_GENERIC_DQ, False),
+                             ("dv_blocks", _lib.BWD_SMALL_BLOCKS, False),
+                             ("dv_blocks_f32", _lib.BWD_SMALL_BLOCKS, True), ("dv_f32", 0, True)):
+        dq, dv, dT = ops.maxmean_bwd(qd, vd, idx, g, clip, scale, Tt, dv_f32=f32, flags=flags)
+        outs[name] = (dq, dv)
+        assert rel_err(dq.cpu(), ref["dq"]) < 4e-3, name
+        assert rel_err(dv.cpu(), ref["dv"]) < (1e-5 if f32 else 4e-3), name
+    for name in ("dq_l1", "dq_l1_nopf", "dq_generic"):          # same summation order: bit-identical
+        assert torch.equal(outs[name][0], outs["default"][0]), name
+    assert torch.equal(outs["dv_f32"][1].to(torch.bfloat16), outs["default"][1])
+    if masked:                                                   # padded tokens: exactly zero gradient
+        assert outs["default"][0][mask.cuda() == 0].abs().max().item() == 0.0
+
+
 def test_masked_text_shape_cfg3_slice():
     """cfg 3 flavour: 77 text tokens with ragged right-padded masks (n_i in [8,77])."""
     B, Nq, Nv, D = 48, 77, 256, 512

@@ -38,23 +38,26 @@ def rel(a, b):
 def main():
     cfg = dict(bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"])
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-    if len(sys.argv) > 3:
-        cfg["B"] = int(sys.argv[3])
+    Bq = int(sys.argv[3]) if len(sys.argv) > 3 else cfg["B"]       # local query rows (a rank's shard)
+    Bv = int(sys.argv[4]) if len(sys.argv) > 4 else Bq             # images (the all-gathered batch)
     dev = torch.device("cuda", 0)
-    (q, v, mask), = bench.make_device_inputs(cfg, cfg["B"], 1234, dev, 1)
-    B, Nq, D = q.shape
+    (q, _, mask), = bench.make_device_inputs(cfg, Bq, 1234, dev, 1)
+    (_, v, _), = bench.make_device_inputs(cfg, Bv, 4321, dev, 1)
+    _, Nq, D = q.shape
     Nv = v.shape[1]
-    scale = ops.row_scale(mask, B, Nq, dev)
+    B = Bv
+    scale = ops.row_scale(mask, Bq, Nq, dev)
     T = torch.tensor(1.5, device=dev)
     clip, idx = ops.maxmean_fwd(q, v, scale, T)
     row_lse, col_part = ops.infonce_partial(clip, B, 0)
     g, sums = ops.infonce_finish(clip, B, 0, row_lse, col_part.reshape(1, 2, B))
-    print(f"shape B={B} Nq={Nq} Nv={Nv} D={D} masked={mask is not None}  loss={sums[0].item() / (2 * B):.6f}")
+    print(f"shape Bq={Bq} Bv={Bv} Nq={Nq} Nv={Nv} D={D} masked={mask is not None}  block loss sum={sums[0].item() / (2 * B):.6f}")
 
     t_fwd = timeit(lambda: ops.maxmean_fwd(q, v, scale, T), iters)
     t_nce = timeit(lambda: ops.infonce_finish(clip, B, 0, *ops.infonce_partial(clip, B, 0)[:1],
                                                col_part.reshape(1, 2, B)), iters)
-    print(f"fwd {t_fwd:.3f} ms   infonce {t_nce:.3f} ms")
+    tf = 2.0 * Bv * (mask.sum().item() if mask is not None else Bq * Nq) * Nv * D / 1e12
+    print(f"fwd {t_fwd:.3f} ms ({tf / t_fwd * 1e3:.0f} TFLOP/s)   infonce {t_nce:.3f} ms")
 
     def bwd(dq, dv, flags):
         return ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=dq, need_dv=dv, need_dT=False, flags=flags)
@@ -74,7 +77,8 @@ def main():
     print("dv default vs generic rel diff", rel(outs["dv default"], outs["dv generic"]),
           " exact:", torch.equal(outs["dv default"], outs["dv generic"]))
     t_all = timeit(lambda: ops.maxmean_bwd(q, v, idx, g, clip, scale, T), iters)
-    print(f"bwd (dq+dv+dT) {t_all:.3f} ms    fwd+nce+bwd {t_fwd + t_nce + t_all:.3f} ms")
+    tot = t_fwd + t_nce + t_all
+    print(f"bwd (dq+dv+dT) {t_all:.3f} ms    fwd+nce+bwd {tot:.3f} ms  = {Bq * Bv / tot / 1e3:.2f} M pairs/s per GPU")
 
 
 if __name__ == "__main__":

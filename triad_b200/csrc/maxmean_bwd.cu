@@ -62,6 +62,27 @@ template <> struct StoreAs<__nv_bfloat16, 8> {
     __device__ static __forceinline__ void put(__nv_bfloat16* p, const float (&f)[8]) { Vec16<__nv_bfloat16>::store(p, f); }
 };
 
+template <typename OutT, int E> struct LoadAs;
+template <int E> struct LoadAs<float, E> {
+    __device__ static __forceinline__ void get(const float* p, float (&f)[E]) {
+#pragma unroll
+        for (int c = 0; c < E; c += 4) {
+            const float4 u = *reinterpret_cast<const float4*>(p + c);
+            f[c] = u.x; f[c + 1] = u.y; f[c + 2] = u.z; f[c + 3] = u.w;
+        }
+    }
+};
+template <> struct LoadAs<__nv_bfloat16, 8> {
+    __device__ static __forceinline__ void get(const __nv_bfloat16* p, float (&f)[8]) { Vec16<__nv_bfloat16>::load(p, f); }
+};
+
+// fp32 scratch -> output dtype (used when dv is accumulated over several query blocks)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+dv_convert_kernel(const float* __restrict__ src, size_t n, OutT* __restrict__ dst) {
+    for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < n; k += (size_t)gridDim.x * 256) dst[k] = (OutT)src[k];
+}
+
 // ---------------------------------------------------------------------------------------
 // dq (generic gather): one CTA = 32 consecutive token rows; 8 warps x 4 rows; lanes own
 // 16-byte chunks of D; winners and weights of 32 images at a time are staged in shared memory.
@@ -169,8 +190,8 @@ struct __align__(8) DvEntry { uint32_t row; float w; };
 
 template <typename IdxT>
 __global__ void __launch_bounds__(kSortWarps * 32)
-dv_count_kernel(const IdxT* __restrict__ idx, int j0, int nj, int Bq, int Nq, int Nv, int nq_pad,
-                uint32_t* __restrict__ cnt) {
+dv_count_kernel(const IdxT* __restrict__ idx, const float* __restrict__ row_scale, size_t img_pitch,
+                int j0, int nj, int Bq, int Nq, int Nv, int nq_pad, uint32_t* __restrict__ cnt) {
     extern __shared__ uint32_t sm_cnt[];                       // [kSortWarps][Nv]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * kSortWarps + warp;           // (jl, c)
@@ -181,9 +202,10 @@ dv_count_kernel(const IdxT* __restrict__ idx, int j0, int nj, int Bq, int Nq, in
         const int jl = item / kSortGroups, c = item % kSortGroups;
         const int qper = (Bq + kSortGroups - 1) / kSortGroups;
         const int i0 = c * qper, i1 = min(Bq, i0 + qper);
-        const IdxT* base = idx + (size_t)(j0 + jl) * Bq * nq_pad;
+        const IdxT* base = idx + (size_t)(j0 + jl) * img_pitch;
         for (int i = i0; i < i1; ++i)
-            for (int a = lane; a < Nq; a += 32) atomicAdd(&my[(int)base[(size_t)i * nq_pad + a]], 1u);
+            for (int a = lane; a < Nq; a += 32)
+                if (row_scale[i * Nq + a] != 0.f) atomicAdd(&my[(int)base[(size_t)i * nq_pad + a]], 1u);
         __syncwarp();
         uint32_t* out = cnt + ((size_t)jl * kSortGroups + c) * Nv;
         for (int p = lane; p < Nv; p += 32) out[p] = my[p];
@@ -233,7 +255,7 @@ dv_offsets_kernel(const uint32_t* __restrict__ cnt, int nj, int Nv, uint32_t* __
 template <typename IdxT>
 __global__ void __launch_bounds__(kSortWarps * 32)
 dv_scatter_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g,
-                       const float* __restrict__ row_scale, const uint32_t* __restrict__ start,
+                       const float* __restrict__ row_scale, const uint32_t* __restrict__ start, size_t img_pitch,
                        int j0, int nj, int Bq, int Bv, int Nq, int Nv, int nq_pad, size_t Mrows,
                        DvEntry* __restrict__ entries) {
     extern __shared__ uint32_t sm_cur[];                       // [kSortWarps][Nv]
@@ -248,14 +270,16 @@ dv_scatter_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g
     const int j = j0 + jl;
     const int qper = (Bq + kSortGroups - 1) / kSortGroups;
     const int i0 = c * qper, i1 = min(Bq, i0 + qper);
-    const IdxT* base = idx + (size_t)j * Bq * nq_pad;
+    const IdxT* base = idx + (size_t)j * img_pitch;
     DvEntry* out = entries + (size_t)jl * Mrows;
     const uint32_t lt = (1u << lane) - 1u;
     for (int i = i0; i < i1; ++i) {
         const float gij = g[(size_t)i * Bv + j];
         for (int a0 = 0; a0 < Nq; a0 += 32) {
             const int a = a0 + lane;
-            const bool valid = a < Nq;
+            // rows with zero weight (padded text tokens, model.py:510) contribute nothing: not listed
+            const float rs = (a < Nq) ? row_scale[i * Nq + a] : 0.f;
+            const bool valid = rs != 0.f;
             const int p = valid ? (int)base[(size_t)i * nq_pad + a] : -1 - lane;   // distinct dummies
             const uint32_t peers = __match_any_sync(0xffffffffu, p);
             uint32_t pos = 0;
@@ -265,7 +289,7 @@ dv_scatter_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g
             __syncwarp();
             if (valid) {
                 const int r = i * Nq + a;
-                DvEntry e; e.row = (uint32_t)r; e.w = row_scale[r] * gij;
+                DvEntry e; e.row = (uint32_t)r; e.w = rs * gij;
                 out[pos] = e;
             }
         }
@@ -285,7 +309,7 @@ template <typename T, typename OutT>
 __global__ void __launch_bounds__(256)
 dv_gather_kernel(const T* __restrict__ q, const DvEntry* __restrict__ entries, const uint32_t* __restrict__ seg,
                  const float* __restrict__ Tptr, int j0, int nj, int Nv, int D, int wps, size_t Mrows,
-                 OutT* __restrict__ dv) {
+                 int accumulate, OutT* __restrict__ dv) {
     constexpr int E = Vec16<T>::kElems;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * 8 + warp;
@@ -332,7 +356,14 @@ dv_gather_kernel(const T* __restrict__ q, const DvEntry* __restrict__ entries, c
         float o[E];
 #pragma unroll
         for (int c = 0; c < E; ++c) o[c] = acc[c] * Tval;
-        StoreAs<OutT, E>::put(dv + ((size_t)(j0 + jl) * Nv + p) * D + ch * E, o);
+        OutT* dst = dv + ((size_t)(j0 + jl) * Nv + p) * D + ch * E;
+        if (accumulate) {                       // later query blocks add to the fp32 partial of the earlier ones
+            float prev[E];
+            LoadAs<OutT, E>::get(dst, prev);
+#pragma unroll
+            for (int c = 0; c < E; ++c) o[c] += prev[c];
+        }
+        StoreAs<OutT, E>::put(dst, o);
     }
 }
 
@@ -358,14 +389,32 @@ dT_kernel(const float* __restrict__ g, const float* __restrict__ clip, size_t n,
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// The dv pass is tiled twice so that its working sets stay on chip whatever the batch size:
+//   * over QUERY BLOCKS of <= kDvBlockBytes of q rows (64 MB: the block a warp gathers from stays
+//     L2-resident; at B=256 the whole q is one block) — later blocks accumulate into the output;
+//   * over IMAGE BATCHES that bound the sorted entry list to ~1 GiB.
+constexpr size_t kDvBlockBytes = (size_t)64 << 20;
 struct DvPlan {
-    int jb;                 // images sorted per batch (bounds the entry list to ~1 GiB)
-    size_t off_cnt, off_start, off_seg, off_entries, total;
+    int jb;                 // images per batch
+    int qb;                 // queries per block
+    int nblk;               // number of query blocks
+    bool scratch;           // fp32 scratch needed (several blocks and a non-fp32 output)
+    size_t off_cnt, off_start, off_seg, off_entries, off_scratch, total;
 };
-static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv) {
+static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool out_f32, size_t block_bytes = kDvBlockBytes) {
     DvPlan pl;
-    const size_t M = (size_t)Bq * Nq;
-    size_t jb = ((size_t)1 << 30) / (M * sizeof(DvEntry));
+    size_t qb = block_bytes / ((size_t)Nq * D * elt_bytes);
+    if (qb < 1) qb = 1;
+    if (qb > (size_t)Bq) qb = Bq;
+    pl.qb = (int)qb;
+    pl.nblk = (int)(((size_t)Bq + qb - 1) / qb);
+    pl.scratch = pl.nblk > 1 && !out_f32;
+    const size_t Mb = qb * Nq;                                       // rows per block
+    size_t jb = ((size_t)1 << 30) / (Mb * sizeof(DvEntry));
+    if (pl.scratch) {                                                // keep the fp32 scratch <= 256 MB
+        const size_t js = ((size_t)256 << 20) / ((size_t)Nv * D * 4);
+        if (jb > js) jb = js;
+    }
     if (jb < 1) jb = 1;
     if (jb > (size_t)Bv) jb = Bv;
     pl.jb = (int)jb;
@@ -373,7 +422,8 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv) {
     pl.off_cnt = o;     o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_start = o;   o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_seg = o;     o += align_up(jb * ((size_t)Nv + 1) * 4, 256);
-    pl.off_entries = o; o += align_up(jb * M * sizeof(DvEntry), 256);
+    pl.off_entries = o; o += align_up(jb * Mb * sizeof(DvEntry), 256);
+    pl.off_scratch = o; o += pl.scratch ? align_up(jb * (size_t)Nv * D * 4, 256) : 0;
     pl.total = o;
     return pl;
 }
@@ -410,32 +460,53 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
         TRIAD_LAUNCH_CHECK("dq_gather_kernel");
     }
     if (dv) {
-        const DvPlan pl = dv_plan(Bq, Bv, Nq, Nv);
+        const bool out_f32 = dv_f32 || sizeof(T) == 4;
+        // TRIAD_BWD_SMALL_BLOCKS (tests): 64 KB query blocks, so small shapes exercise the multi-block path
+        const DvPlan pl = dv_plan(Bq, Bv, Nq, Nv, D, (int)sizeof(T), out_f32,
+                                  (bwd_flags & TRIAD_BWD_SMALL_BLOCKS) ? ((size_t)64 << 10) : kDvBlockBytes);
         uint32_t* cnt = (uint32_t*)((char*)ws + pl.off_cnt);
         uint32_t* start = (uint32_t*)((char*)ws + pl.off_start);
         uint32_t* seg = (uint32_t*)((char*)ws + pl.off_seg);
         DvEntry* entries = (DvEntry*)((char*)ws + pl.off_entries);
+        float* scratch = (float*)((char*)ws + pl.off_scratch);
         const size_t smem = (size_t)kSortWarps * Nv * 4;
         if (smem > 48 * 1024) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: Nv too large for the dv sort");
-        const bool out_f32 = dv_f32 || sizeof(T) == 4;
+        const size_t img_pitch = (size_t)Bq * nq_pad;
+        const int wps = ceil_div(D / E, 32);                                       // warps per segment
         for (int j0 = 0; j0 < Bv; j0 += pl.jb) {
             const int nj = (Bv - j0 < pl.jb) ? (Bv - j0) : pl.jb;
             const int sort_grid = ceil_div(nj * kSortGroups, kSortWarps);
-            dv_count_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>((const IdxT*)idx, j0, nj, Bq, Nq, Nv, nq_pad, cnt);
-            TRIAD_LAUNCH_CHECK("dv_count_kernel");
-            dv_offsets_kernel<<<nj, 1024, 0, st>>>(cnt, nj, Nv, start, seg);
-            TRIAD_LAUNCH_CHECK("dv_offsets_kernel");
-            dv_scatter_sort_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(
-                (const IdxT*)idx, g, row_scale, start, j0, nj, Bq, Bv, Nq, Nv, nq_pad, (size_t)M, entries);
-            TRIAD_LAUNCH_CHECK("dv_scatter_sort_kernel");
-            const int wps = ceil_div(D / E, 32);                                   // warps per segment
             const long long nwarps = (long long)nj * Nv * wps;
             const unsigned ggrid = (unsigned)((nwarps + 7) / 8);
-            if (out_f32)
-                dv_gather_kernel<T, float><<<ggrid, 256, 0, st>>>((const T*)q, entries, seg, Tp, j0, nj, Nv, D, wps, (size_t)M, (float*)dv);
-            else
-                dv_gather_kernel<T, T><<<ggrid, 256, 0, st>>>((const T*)q, entries, seg, Tp, j0, nj, Nv, D, wps, (size_t)M, (T*)dv);
-            TRIAD_LAUNCH_CHECK("dv_gather_kernel");
+            for (int b = 0; b < pl.nblk; ++b) {
+                const int q0 = b * pl.qb;
+                const int nq = (Bq - q0 < pl.qb) ? (Bq - q0) : pl.qb;
+                const size_t Mb = (size_t)nq * Nq;
+                const IdxT* idx_b = (const IdxT*)idx + (size_t)q0 * nq_pad;
+                const float* rs_b = row_scale + (size_t)q0 * Nq;
+                const float* g_b = g + (size_t)q0 * Bv;
+                const T* q_b = (const T*)q + (size_t)q0 * Nq * D;
+                dv_count_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(idx_b, rs_b, img_pitch, j0, nj, nq, Nq, Nv, nq_pad, cnt);
+                TRIAD_LAUNCH_CHECK("dv_count_kernel");
+                dv_offsets_kernel<<<nj, 1024, 0, st>>>(cnt, nj, Nv, start, seg);
+                TRIAD_LAUNCH_CHECK("dv_offsets_kernel");
+                dv_scatter_sort_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(
+                    idx_b, g_b, rs_b, start, img_pitch, j0, nj, nq, Bv, Nq, Nv, nq_pad, Mb, entries);
+                TRIAD_LAUNCH_CHECK("dv_scatter_sort_kernel");
+                if (pl.scratch)          // accumulate this image batch in fp32 scratch (local image index), convert at the end
+                    dv_gather_kernel<T, float><<<ggrid, 256, 0, st>>>(q_b, entries, seg, Tp, 0, nj, Nv, D, wps, Mb, b > 0, scratch);
+                else if (out_f32)
+                    dv_gather_kernel<T, float><<<ggrid, 256, 0, st>>>(q_b, entries, seg, Tp, j0, nj, Nv, D, wps, Mb, b > 0, (float*)dv);
+                else
+                    dv_gather_kernel<T, T><<<ggrid, 256, 0, st>>>(q_b, entries, seg, Tp, j0, nj, Nv, D, wps, Mb, b > 0, (T*)dv);
+                TRIAD_LAUNCH_CHECK("dv_gather_kernel");
+            }
+            if (pl.scratch) {
+                const size_t n = (size_t)nj * Nv * D;
+                dv_convert_kernel<T><<<(unsigned)((n + 2047) / 2048 > 4096 ? 4096 : (n + 2047) / 2048), 256, 0, st>>>(
+                    scratch, n, (T*)dv + (size_t)j0 * Nv * D);
+                TRIAD_LAUNCH_CHECK("dv_convert_kernel");
+            }
         }
     }
     if (dT) {
@@ -450,9 +521,16 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
 using namespace triad;
 
 extern "C" size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype) {
-    (void)D; (void)dtype;
-    if (Bq <= 0 || Bv <= 0 || Nq <= 0 || Nv <= 0) return 0;
-    return dv_plan(Bq, Bv, Nq, Nv).total;
+    if (Bq <= 0 || Bv <= 0 || Nq <= 0 || Nv <= 0 || D <= 0) return 0;
+    // the caller may ask for dv in `dtype` (fp32 scratch when several query blocks) or as an fp32 partial
+    const int eb = dtype == TRIAD_DTYPE_BF16 ? 2 : 4;
+    size_t best = 0;
+    for (int f32 = 0; f32 < 2; ++f32)
+        for (int small = 0; small < 2; ++small) {
+            const size_t t = dv_plan(Bq, Bv, Nq, Nv, D, eb, f32 != 0, small ? ((size_t)64 << 10) : kDvBlockBytes).total;
+            if (t > best) best = t;
+        }
+    return best;
 }
 
 extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
