@@ -234,6 +234,31 @@ def test_backward_variants_agree(masked):
         assert outs["default"][0][mask.cuda() == 0].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("flags", [0, FWD_1CTA, FWD_SIMT])
+@pytest.mark.parametrize("Nv", [257, 600, 1024])
+def test_more_than_256_patches(flags, Nv):
+    """High-resolution galleries (cfg 5: 1024 patches per image): the tcgen05 kernel walks an image as
+    256-patch sub-tiles with a running (rounded max, first argmax) per row; indices are uint16.  Ties
+    between sub-tiles (duplicated patches) must resolve to the first index."""
+    from triad_b200 import ops
+    B, Nq, D = 5, 70, 128
+    q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=90 + Nv)
+    v[:, Nv - 3] = v[:, 1]            # exact duplicates in different sub-tiles -> exact ties
+    v[:, 300 % Nv] = v[:, 7]
+    ref = O.contrastive_step_closed_form(q, v, 1.5)
+    m = _model(1.5, flags)
+    qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    clip, tok = m.compute_all_similarities_av(qd, vd)
+    assert tok.idx_t.dtype == torch.uint16
+    con = m.compute_contrastive_loss_av(clip, tok)[1]
+    con.backward()
+    n_bad, worst = _near_tie_report(q, v, 1.5, tok.argmax().cpu(), ref["idx"])
+    assert n_bad <= 2 and worst < 2 ** -7
+    assert rel_err(tok.clip.detach().cpu(), ref["clip"]) < 5e-5
+    assert abs(con.item() - ref["loss"].item()) < 1e-5 * ref["loss"].item()
+    assert rel_err(qd.grad.cpu(), ref["dq"]) < 4e-3 and rel_err(vd.grad.cpu(), ref["dv"]) < 4e-3
+
+
 def test_masked_text_shape_cfg3_slice():
     """cfg 3 flavour: 77 text tokens with ragged right-padded masks (n_i in [8,77])."""
     B, Nq, Nv, D = 48, 77, 256, 512

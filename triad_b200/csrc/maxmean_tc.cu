@@ -6,7 +6,9 @@
 // accumulator tiles in tensor memory:
 //
 //   * rows   = query tokens, flattened over the batch (M = Bq*Nq), 128 per CTA = the 128 TMEM lanes;
-//   * cols   = the Nv patches of ONE image (UMMA N = Nv rounded up to 16, <= 256);
+//   * cols   = the Nv patches of ONE image (UMMA N = Nv rounded up to 16, <= 256); images with more
+//              patches (high-resolution DINOv2: 1024) are walked as consecutive 256-patch SUB-TILES and
+//              the epilogue keeps a running (rounded max, first argmax) per row across them;
 //   * K      = D (<= 512) in 64-element (128-byte, SWIZZLE_128B) k-blocks.
 //
 // Work decomposition (persistent, one CTA or CTA pair per SM / SM pair):
@@ -52,7 +54,9 @@ constexpr uint32_t kSmemBytes = kQBytes + kVRingBytes + kBarBytes + 1024;   // +
 
 struct Params {
     int M, Bv, Nq, Nv;
-    int n_umma;        // UMMA N (Nv rounded up to 16)
+    int n_umma;        // UMMA N (Nv rounded up to 16; 256 when the image is split into sub-tiles)
+    int n_sub;         // 256-patch sub-tiles per image (1 when Nv <= 256)
+    int idx16;         // idx elements are uint16 (Nv > 256)
     int num_kb;        // D / 64
     int n_m;           // number of (128*cta_group)-row tiles
     int C;             // images per chunk
@@ -90,7 +94,9 @@ __device__ __forceinline__ Tile decode_tile(uint32_t L, int n_m, int Bv, int C) 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int kCtaGroup>
+// kSub = false: one accumulator tile per image (Nv <= 256), the training shapes' hot path;
+// kSub = true : n_sub 256-patch sub-tiles per image.
+template <int kCtaGroup, bool kSub>
 __global__ void __launch_bounds__(kThreads, 1)
 maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
                   const Params p) {
@@ -120,9 +126,11 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t cluster_id = blockIdx.x / kCtaGroup;
     const uint32_t n_clusters = gridDim.x / kCtaGroup;
 
+    // work items are (m-tile, image) pairs; each is n_sub consecutive accumulator tiles
     const uint32_t total = (uint32_t)p.n_m * (uint32_t)p.Bv;
     const uint32_t L_begin = (uint32_t)(((unsigned long long)total * cluster_id) / n_clusters);
     const uint32_t L_end = (uint32_t)(((unsigned long long)total * (cluster_id + 1)) / n_clusters);
+    const int n_sub = kSub ? p.n_sub : 1;
 
     const int n_half = p.n_umma / kCtaGroup;                    // patch rows this CTA loads per image
     const uint32_t v_tx_bytes = (uint32_t)n_half * kBlockK * 2u;
@@ -158,18 +166,21 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     qe_phase ^= 1;
                     if (!ok) break;
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    if (new_m) {
-                        if (is_leader) mbar_expect_tx(bar_q_full + 8 * kb, kQkbBytes * kCtaGroup);
-                        tma_load_2d<kCtaGroup>(q_smem + kb * kQkbBytes, &tmap_q, q_full_sig + 8 * kb,
-                                               kb * kBlockK, t.m * kTileRows + (int)cta_rank * kBlockM);
+                for (int sb = 0; sb < n_sub && ok; ++sb) {
+                    for (int kb = 0; kb < p.num_kb; ++kb) {
+                        if (new_m && sb == 0) {
+                            if (is_leader) mbar_expect_tx(bar_q_full + 8 * kb, kQkbBytes * kCtaGroup);
+                            tma_load_2d<kCtaGroup>(q_smem + kb * kQkbBytes, &tmap_q, q_full_sig + 8 * kb,
+                                                   kb * kBlockK, t.m * kTileRows + (int)cta_rank * kBlockM);
+                        }
+                        ok = mbar_wait(bar_v_empty + 8 * stage, phase ^ 1, p.abort_flag, 2);
+                        if (!ok) break;
+                        if (is_leader) mbar_expect_tx(bar_v_full + 8 * stage, v_tx_bytes * kCtaGroup);
+                        // patches beyond Nv (last sub-tile) are zero-filled by TMA and masked in the epilogue
+                        tma_load_3d<kCtaGroup>(v_smem + stage * kVStageBytes, &tmap_v, v_full_sig + 8 * stage,
+                                               kb * kBlockK, sb * kMaxN + (int)cta_rank * n_half, t.j);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    ok = mbar_wait(bar_v_empty + 8 * stage, phase ^ 1, p.abort_flag, 2);
-                    if (!ok) break;
-                    if (is_leader) mbar_expect_tx(bar_v_full + 8 * stage, v_tx_bytes * kCtaGroup);
-                    tma_load_3d<kCtaGroup>(v_smem + stage * kVStageBytes, &tmap_v, v_full_sig + 8 * stage,
-                                           kb * kBlockK, (int)cta_rank * n_half, t.j);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 prev_m = t.m;
             }
@@ -180,16 +191,17 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t idesc = make_idesc(kTileRows, p.n_umma);
             int stage = 0; uint32_t phase = 0, qf_phase = 0; int prev_m = -1; uint32_t t_cnt = 0;
             bool ok = true;
-            for (uint32_t L = L_begin; L < L_end && ok; ++L, ++t_cnt) {
+            for (uint32_t L = L_begin; L < L_end && ok; ++L) {
                 const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
                 const bool new_m = (t.m != prev_m);
+              for (int sb = 0; sb < n_sub && ok; ++sb, ++t_cnt) {
                 const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
                 ok = mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1, p.abort_flag, 3);
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kMaxN;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
-                    if (new_m) { ok = mbar_wait(bar_q_full + 8 * kb, qf_phase, p.abort_flag, 4); if (!ok) break; }
+                    if (new_m && sb == 0) { ok = mbar_wait(bar_q_full + 8 * kb, qf_phase, p.abort_flag, 4); if (!ok) break; }
                     ok = mbar_wait(bar_v_full + 8 * stage, phase, p.abort_flag, 5);
                     if (!ok) break;
                     tc_fence_after();
@@ -205,6 +217,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
                 if (!ok) break;
                 umma_commit<kCtaGroup>(bar_t_full + 8 * acc);            // accumulator ready (both CTAs)
+              }
+                if (!ok) break;
                 bool next_new_m = true;
                 if (L + 1 < L_end) next_new_m = (decode_tile(L + 1, p.n_m, p.Bv, p.C).m != t.m);
                 if (next_new_m) umma_commit<kCtaGroup>(bar_q_empty);     // query tile may be overwritten
@@ -219,11 +233,12 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         float Tval = *p.T;
         if (p.inv_T) Tval = 1.0f / Tval;
         const int nch = p.n_umma >> 4;
-        const int Nv = p.Nv;
         int prev_m = -1; float rs = 0.f; uint32_t t_cnt = 0;
         size_t idx_off = 0;                       // (i*nq_pad + a) of this thread's row
         const size_t idx_pitch = (size_t)(p.M / p.Nq) * p.nq_pad;
-        for (uint32_t L = L_begin; L < L_end; ++L, ++t_cnt) {
+        float R_run = 0.f; int best_run = 0;      // running (rounded max, first argmax) across the sub-tiles of an image
+        bool alive = true;
+        for (uint32_t L = L_begin; L < L_end && alive; ++L) {
             const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
             const int row0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;
             const int r = row0 + lane;
@@ -233,11 +248,13 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 idx_off = (size_t)qi * p.nq_pad + (r - qi * p.Nq);
                 prev_m = t.m;
             }
+          for (int sb = 0; sb < n_sub; ++sb, ++t_cnt) {
             const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
             bool ok = mbar_wait(bar_t_full + 8 * acc, acc_phase, p.abort_flag, 6);
             ok = __all_sync(0xffffffffu, ok);
-            if (!ok) break;
+            if (!ok) { alive = false; break; }
             tc_fence_after();
+            const int Nv = p.Nv - sb * kMaxN;                // patches of this sub-tile that exist (may exceed 256)
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxN;
 
             // ---- pass 1: row maximum over the Nv raw accumulators ----
@@ -280,8 +297,16 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if constexpr (kCtaGroup == 2) mbar_arrive_cluster(t_empty_sig + 8 * acc);
                 else mbar_arrive_local(bar_t_empty + 8 * acc);
             }
-            if (p.idx != nullptr && r < p.M) p.idx[(size_t)t.j * idx_pitch + idx_off] = (uint8_t)best;
-            const float val = (r < p.M) ? R * rs : 0.f;
+            // Equal rounded maxima in two sub-tiles: the earlier one holds the first index (torch.max), and
+            // inside a sub-tile `best` already is the first column of that rounded value.
+            if (sb == 0 || R > R_run) { R_run = R; best_run = best + sb * kMaxN; }
+          }
+            if (!alive) break;
+            if (p.idx != nullptr && r < p.M) {
+                if (p.idx16) reinterpret_cast<uint16_t*>(p.idx)[(size_t)t.j * idx_pitch + idx_off] = (uint16_t)best_run;
+                else p.idx[(size_t)t.j * idx_pitch + idx_off] = (uint8_t)best_run;
+            }
+            const float val = (r < p.M) ? R_run * rs : 0.f;
             store_group_partials(p.part, t.j, row0 >> 5, p.G, p.S, row0, p.M, p.Nq, val, lane);
         }
     }
@@ -337,9 +362,9 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
     return encode_tmap_bf16(map, base, rank, dims, strides, box, true);
 }
 
-template <int kCtaGroup>
+template <int kCtaGroup, bool kSub>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& p, int n_clusters, cudaStream_t st) {
-    auto kern = maxmean_tc_kernel<kCtaGroup>;
+    auto kern = maxmean_tc_kernel<kCtaGroup, kSub>;
     static bool attr_set = false;
     if (!attr_set) {
         TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -363,16 +388,17 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& 
 
 }  // namespace tc
 
-bool tc_supported(int Nv, int D) { return Nv >= 1 && Nv <= tc::kMaxN && D % tc::kBlockK == 0 && D >= tc::kBlockK && D <= tc::kMaxKB * tc::kBlockK; }
+bool tc_supported(int Nv, int D) { return Nv >= 1 && Nv <= 65535 && D % tc::kBlockK == 0 && D >= tc::kBlockK && D <= tc::kMaxKB * tc::kBlockK; }
 
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
                       float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st) {
     using namespace tc;
-    if (!tc_supported(Nv, D)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: needs Nv <= 256 and D in {64,...,512} (multiple of 64)");
+    if (!tc_supported(Nv, D)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: needs D in {64,...,512} (multiple of 64)");
     const int tile_rows = kBlockM * cta_group;
     const int n_m = ceil_div(M, tile_rows);
-    if ((long long)n_m * Bv >= 0x7fffffffLL) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: too many tiles");
+    const int n_sub = ceil_div(Nv, kMaxN);
+    if ((long long)n_m * Bv * n_sub >= 0x7fffffffLL) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: too many tiles");
 
     int dev = 0, sms = 0;
     TRIAD_CUDA_CHECK(cudaGetDevice(&dev));
@@ -380,7 +406,9 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
 
     Params p;
     p.M = M; p.Bv = Bv; p.Nq = Nq; p.Nv = Nv;
-    p.n_umma = (Nv + 15) / 16 * 16;
+    p.n_umma = n_sub > 1 ? kMaxN : (Nv + 15) / 16 * 16;
+    p.n_sub = n_sub;
+    p.idx16 = Nv > 256;
     p.num_kb = D / kBlockK;
     p.n_m = n_m;
     // image chunk: keep all of V L2-resident when it is small, otherwise walk 64 images at a time
@@ -411,8 +439,8 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     int n_clusters = sms / cta_group;
     if ((long long)n_clusters > total) n_clusters = (int)total;
     if (n_clusters < 1) n_clusters = 1;
-    if (cta_group == 2) return launch_t<2>(mq, mv, p, n_clusters, st);
-    return launch_t<1>(mq, mv, p, n_clusters, st);
+    if (n_sub > 1) return cta_group == 2 ? launch_t<2, true>(mq, mv, p, n_clusters, st) : launch_t<1, true>(mq, mv, p, n_clusters, st);
+    return cta_group == 2 ? launch_t<2, false>(mq, mv, p, n_clusters, st) : launch_t<1, false>(mq, mv, p, n_clusters, st);
 }
 
 }  // namespace triad
