@@ -72,6 +72,40 @@ struct Params {
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// maximum of one 32-column chunk of a row; columns >= Nv (TMA zero fill / stale TMEM) do not take part
+__device__ __forceinline__ float chunk_max32(const uint32_t (&r)[32], int col0, int Nv) {
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+    if (col0 + 32 > Nv) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) if (col0 + e >= Nv) v[e] = -INFINITY;
+    }
+    float m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                       // four independent chains of 8
+        m[k] = fmax3(v[8 * k], v[8 * k + 1], v[8 * k + 2]);
+        m[k] = fmax3(m[k], v[8 * k + 3], v[8 * k + 4]);
+        m[k] = fmax3(m[k], v[8 * k + 5], v[8 * k + 6]);
+        m[k] = fmaxf(m[k], v[8 * k + 7]);
+    }
+    return fmaxf(fmax3(m[0], m[1], m[2]), m[3]);
+}
+
+// best = lowest column of this chunk with value >= theta, if any (columns >= Nv never qualify)
+__device__ __forceinline__ void first_ge32(const uint32_t (&r)[32], int col0, int Nv, float theta, int& best) {
+    const int lim = Nv - col0;                          // >= 32 for every chunk but the last partial one
+    int b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                       // four independent chains of 8 (descending: lowest sticks)
+        b[k] = 64;
+#pragma unroll
+        for (int e = 7; e >= 0; --e) if (__uint_as_float(r[8 * k + e]) >= theta) b[k] = 8 * k + e;
+    }
+    const int lo = min(min(b[0], b[1]), min(b[2], b[3]));
+    if (lo < min(lim, 32)) best = col0 + lo;            // 64 = "none"; columns >= lim are padding
+}
+
 struct Tile { int m, j; };
 __device__ __forceinline__ Tile decode_tile(uint32_t L, int n_m, int Bv, int C) {
     const uint32_t per_chunk = (uint32_t)n_m * (uint32_t)C;
@@ -232,7 +266,6 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
         float Tval = *p.T;
         if (p.inv_T) Tval = 1.0f / Tval;
-        const int nch = p.n_umma >> 4;
         int prev_m = -1; float rs = 0.f; uint32_t t_cnt = 0;
         size_t idx_off = 0;                       // (i*nq_pad + a) of this thread's row
         const size_t idx_pitch = (size_t)(p.M / p.Nq) * p.nq_pad;
@@ -257,37 +290,46 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const int Nv = p.Nv - sb * kMaxN;                // patches of this sub-tile that exist (may exceed 256)
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxN;
 
-            // ---- pass 1: row maximum over the Nv raw accumulators ----
-            float mx0 = -INFINITY, mx1 = -INFINITY;
-            for (int c = 0; c < nch; ++c) {
-                float v[16];
-                tmem_ld16(taddr + c * 16, v);
+            // ---- pass 1: row maximum over the raw accumulators.  32-column loads, software pipelined
+            //      (chunk c+1 in flight while chunk c is reduced), four independent FMNMX3 chains per chunk.
+            //      All kMaxN/32 chunks are always loaded — columns >= n_umma hold stale but allocated TMEM and
+            //      are masked by Nv — which keeps every load unconditional (see tmem_ld32_raw). ----
+            constexpr int kCh = kMaxN / 32;
+            float mx = -INFINITY;
+            {
+                uint32_t bufA[32], bufB[32];
+                tmem_ld32_raw(taddr, bufA);
                 tmem_wait_ld();
-                if (c * 16 + 16 > Nv) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) if (c * 16 + e >= Nv) v[e] = -INFINITY;
+                for (int c = 0; c < kCh; c += 2) {
+                    tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
+                    mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
+                    tmem_wait_ld();
+                    if (c + 2 < kCh) tmem_ld32_raw(taddr + (c + 2) * 32, bufA);          // compile-time condition
+                    mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
+                    tmem_wait_ld();
                 }
-                mx0 = fmax3(mx0, v[0], v[1]);  mx1 = fmax3(mx1, v[2], v[3]);
-                mx0 = fmax3(mx0, v[4], v[5]);  mx1 = fmax3(mx1, v[6], v[7]);
-                mx0 = fmax3(mx0, v[8], v[9]);  mx1 = fmax3(mx1, v[10], v[11]);
-                mx0 = fmax3(mx0, v[12], v[13]); mx1 = fmax3(mx1, v[14], v[15]);
             }
             float R;
-            const float theta = argmax_threshold<true>(fmaxf(mx0, mx1), Tval, &R);
+            const float theta = argmax_threshold<true>(mx, Tval, &R);
 
-            // ---- pass 2: first column whose accumulator reaches the threshold ----
+            // ---- pass 2: first column whose accumulator reaches the threshold (the reference's first-index
+            //      argmax).  Same pipelined loads, walking the chunks from the last to the first so the lowest
+            //      qualifying column is the one that sticks; inside a chunk four independent 8-column
+            //      compare/select chains instead of one 256-long dependent chain. ----
             int best = 0;
             if (p.idx != nullptr) {
-                for (int c = nch - 1; c >= 0; --c) {
-                    float v[16];
-                    tmem_ld16(taddr + c * 16, v);
+                uint32_t bufA[32], bufB[32];
+                tmem_ld32_raw(taddr + (kCh - 1) * 32, bufA);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = kCh - 1; c >= 0; c -= 2) {
+                    tmem_ld32_raw(taddr + (c - 1) * 32, bufB);
+                    first_ge32(bufA, c * 32, Nv, theta, best);
                     tmem_wait_ld();
-                    if (c * 16 + 16 > Nv) {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) if (c * 16 + e >= Nv) v[e] = -INFINITY;
-                    }
-#pragma unroll
-                    for (int e = 15; e >= 0; --e) if (v[e] >= theta) best = c * 16 + e;
+                    if (c - 2 >= 0) tmem_ld32_raw(taddr + (c - 2) * 32, bufA);           // compile-time condition
+                    first_ge32(bufB, (c - 1) * 32, Nv, theta, best);
+                    tmem_wait_ld();
                 }
             }
             // TMEM stage drained: hand it back to the MMA issuer before touching global memory
