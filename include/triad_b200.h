@@ -53,6 +53,7 @@ extern "C" {
 #define TRIAD_FWD_FORCE_SIMT   1   /* fp32-accumulate CUDA-core kernel (always used for fp32 inputs) */
 #define TRIAD_FWD_FORCE_1CTA   2   /* tcgen05 kernel with cta_group::1 (debug / small shapes)        */
 #define TRIAD_FWD_DIVIDE_BY_T  4   /* S = <q,v> / T (retrieval.py:108) instead of <q,v> * T          */
+#define TRIAD_FWD_SYNC_CHUNKS  8   /* test aid: chunk-synchronous tile order (the V > 96 MB path) with 3-image chunks */
 
 int         triad_abi_version(void);
 const char* triad_status_string(int status);

@@ -15,7 +15,7 @@ from tests.helpers import check_inputs_reproduce, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
-FWD_SIMT, FWD_1CTA = 1, 2
+FWD_SIMT, FWD_1CTA, FWD_SYNC = 1, 2, 8
 
 
 def _model(T, flags=0):
@@ -111,7 +111,7 @@ def _near_tie_report(q, v, T, idx_a, idx_b):
     return len(bad), worst
 
 
-@pytest.mark.parametrize("flags", [0, FWD_1CTA])
+@pytest.mark.parametrize("flags", [0, FWD_1CTA, FWD_SYNC, FWD_SYNC | FWD_1CTA])
 def test_tensor_core_vs_oracle_mid_size(flags):
     """B=24 x 250 x 256 x 512: tcgen05 argmax vs the CPU oracle.  Different fp32 accumulation
     orders can flip a bf16 rounding on an exact-to-the-ulp tie; every disagreement must be such
@@ -234,7 +234,7 @@ def test_backward_variants_agree(masked):
         assert outs["default"][0][mask.cuda() == 0].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("flags", [0, FWD_1CTA, FWD_SIMT])
+@pytest.mark.parametrize("flags", [0, FWD_1CTA, FWD_SIMT, FWD_SYNC])
 @pytest.mark.parametrize("Nv", [257, 600, 1024])
 def test_more_than_256_patches(flags, Nv):
     """High-resolution galleries (cfg 5: 1024 patches per image): the tcgen05 kernel walks an image as

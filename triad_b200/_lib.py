@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtriad_b200.so")
 
 OK = 0
 DTYPE_F32, DTYPE_BF16 = 0, 1
-FWD_DEFAULT, FWD_FORCE_SIMT, FWD_FORCE_1CTA, FWD_DIVIDE_BY_T = 0, 1, 2, 4
+FWD_DEFAULT, FWD_FORCE_SIMT, FWD_FORCE_1CTA, FWD_DIVIDE_BY_T, FWD_SYNC_CHUNKS = 0, 1, 2, 4, 8
 BWD_DEFAULT, BWD_GENERIC_DQ, BWD_GENERIC_DV, BWD_NO_PREFETCH, BWD_DQ_L1, BWD_SMALL_BLOCKS = 0, 1, 2, 4, 8, 16
 
 # name -> (restype, argtypes); must list every symbol of include/triad_b200.h

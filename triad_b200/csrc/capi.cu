@@ -84,7 +84,7 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
     int rc;
     if (use_tc) {
         const int cta_group = (flags & TRIAD_FWD_FORCE_1CTA) ? 1 : 2;
-        rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, st);
+        rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags, st);
     } else {
         rc = launch_maxmean_simt(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, dtype, part, idx, st);
     }

@@ -55,7 +55,7 @@ int launch_maxmean_simt(const void* q, const void* v, const float* row_scale, co
                         float* part, void* idx, cudaStream_t st);   // idx: [Bv][M/Nq][nq_padded(Nq)]
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
-                      float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st);
+                      float* part, void* idx, int* abort_flag, int cta_group, int flags, cudaStream_t st);
 int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
 bool tc_supported(int Nv, int D);
 // tiled dQ of the backward, bf16 only — bwd_dq_tile.cu (TMA/shared-memory gather, and the L1-resident variant)

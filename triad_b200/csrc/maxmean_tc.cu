@@ -60,6 +60,7 @@ struct Params {
     int num_kb;        // D / 64
     int n_m;           // number of (128*cta_group)-row tiles
     int C;             // images per chunk
+    int sync;          // TileIter mode: all clusters walk the same image chunk at the same time
     int G, S;          // partial layout
     int nq_pad;        // idx row pitch per query
     int inv_T;
@@ -125,6 +126,43 @@ __device__ __forceinline__ Tile decode_tile(uint32_t L, int n_m, int Bv, int C) 
     return t;
 }
 
+// The sequence of (m-tile, image) work items of one cluster; the three warp roles walk it in lockstep.
+//   sync == 0: one contiguous range of the chunk-major linearisation (V fits in L2: every cluster may be
+//              anywhere in V, and a cluster changes its query tile as rarely as possible);
+//   sync == 1: every image chunk is cut into one range per cluster, so ALL clusters stream the SAME chunk of
+//              C images at the same time — V is then read from HBM once per pass over the chunk, whatever
+//              its total size (B = 8192: 2.1 GB), at the price of re-loading the (small) query tiles per chunk.
+struct TileIter {
+    uint32_t n_m, Bv, C, cid, ncl, sync;
+    uint32_t L, Lend, j0, cl;
+    __device__ __forceinline__ void range(uint32_t per) {
+        L = (uint32_t)(((unsigned long long)per * cid) / ncl);
+        Lend = (uint32_t)(((unsigned long long)per * (cid + 1)) / ncl);
+    }
+    __device__ __forceinline__ void init(int n_m_, int Bv_, int C_, int sync_, uint32_t cid_, uint32_t ncl_) {
+        n_m = (uint32_t)n_m_; Bv = (uint32_t)Bv_; C = (uint32_t)C_; sync = (uint32_t)sync_; cid = cid_; ncl = ncl_;
+        j0 = 0; cl = min(C, Bv);
+        range(sync ? n_m * cl : n_m * Bv);
+    }
+    __device__ __forceinline__ bool next(Tile& t) {
+        if (!sync) {
+            if (L >= Lend) return false;
+            t = decode_tile(L++, (int)n_m, (int)Bv, (int)C);
+            return true;
+        }
+        while (L >= Lend) {
+            j0 += C;
+            if (j0 >= Bv) return false;
+            cl = min(C, Bv - j0);
+            range(n_m * cl);
+        }
+        t.m = (int)(L / cl);
+        t.j = (int)(j0 + L % cl);
+        ++L;
+        return true;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
@@ -161,9 +199,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t n_clusters = gridDim.x / kCtaGroup;
 
     // work items are (m-tile, image) pairs; each is n_sub consecutive accumulator tiles
-    const uint32_t total = (uint32_t)p.n_m * (uint32_t)p.Bv;
-    const uint32_t L_begin = (uint32_t)(((unsigned long long)total * cluster_id) / n_clusters);
-    const uint32_t L_end = (uint32_t)(((unsigned long long)total * (cluster_id + 1)) / n_clusters);
+    TileIter it;
+    it.init(p.n_m, p.Bv, p.C, p.sync, cluster_id, n_clusters);
     const int n_sub = kSub ? p.n_sub : 1;
 
     const int n_half = p.n_umma / kCtaGroup;                    // patch rows this CTA loads per image
@@ -192,8 +229,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t v_full_sig = (kCtaGroup == 2) ? mapa(bar_v_full, 0) : bar_v_full;
             int stage = 0; uint32_t phase = 0, qe_phase = 0; int prev_m = -1;
             bool ok = true;
-            for (uint32_t L = L_begin; L < L_end && ok; ++L) {
-                const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
+            Tile t;
+            while (ok && it.next(t)) {
                 const bool new_m = (t.m != prev_m);
                 if (new_m && prev_m >= 0) {
                     ok = mbar_wait(bar_q_empty, qe_phase, p.abort_flag, 1);
@@ -225,8 +262,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const uint32_t idesc = make_idesc(kTileRows, p.n_umma);
             int stage = 0; uint32_t phase = 0, qf_phase = 0; int prev_m = -1; uint32_t t_cnt = 0;
             bool ok = true;
-            for (uint32_t L = L_begin; L < L_end && ok; ++L) {
-                const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
+            Tile t;
+            while (ok && it.next(t)) {
                 const bool new_m = (t.m != prev_m);
               for (int sb = 0; sb < n_sub && ok; ++sb, ++t_cnt) {
                 const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
@@ -253,8 +290,9 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 umma_commit<kCtaGroup>(bar_t_full + 8 * acc);            // accumulator ready (both CTAs)
               }
                 if (!ok) break;
-                bool next_new_m = true;
-                if (L + 1 < L_end) next_new_m = (decode_tile(L + 1, p.n_m, p.Bv, p.C).m != t.m);
+                TileIter peek = it;
+                Tile tn;
+                const bool next_new_m = !peek.next(tn) || tn.m != t.m;
                 if (next_new_m) umma_commit<kCtaGroup>(bar_q_empty);     // query tile may be overwritten
                 if (new_m) qf_phase ^= 1;
                 prev_m = t.m;
@@ -271,8 +309,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const size_t idx_pitch = (size_t)(p.M / p.Nq) * p.nq_pad;
         float R_run = 0.f; int best_run = 0;      // running (rounded max, first argmax) across the sub-tiles of an image
         bool alive = true;
-        for (uint32_t L = L_begin; L < L_end && alive; ++L) {
-            const Tile t = decode_tile(L, p.n_m, p.Bv, p.C);
+        Tile t;
+        while (alive && it.next(t)) {
             const int row0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;
             const int r = row0 + lane;
             if (t.m != prev_m) {
@@ -434,7 +472,7 @@ bool tc_supported(int Nv, int D) { return Nv >= 1 && Nv <= 65535 && D % tc::kBlo
 
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
-                      float* part, void* idx, int* abort_flag, int cta_group, cudaStream_t st) {
+                      float* part, void* idx, int* abort_flag, int cta_group, int flags, cudaStream_t st) {
     using namespace tc;
     if (!tc_supported(Nv, D)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: needs D in {64,...,512} (multiple of 64)");
     const int tile_rows = kBlockM * cta_group;
@@ -453,9 +491,17 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     p.idx16 = Nv > 256;
     p.num_kb = D / kBlockK;
     p.n_m = n_m;
-    // image chunk: keep all of V L2-resident when it is small, otherwise walk 64 images at a time
+    // image chunk: keep all of V L2-resident when it is small; up to ~96 MB (cfg 2: 67 MB) the clusters may be
+    // anywhere in V (it still fits the 126 MB L2); beyond that every cluster walks the same ~32 MB chunk.
     const size_t v_bytes = (size_t)Bv * Nv * D * 2;
     p.C = (v_bytes <= (size_t)48 << 20) ? Bv : (Bv < 64 ? Bv : 64);
+    p.sync = 0;
+    if (v_bytes > (size_t)96 << 20 || (flags & TRIAD_FWD_SYNC_CHUNKS)) {
+        size_t c = ((size_t)32 << 20) / ((size_t)Nv * D * 2);
+        if (flags & TRIAD_FWD_SYNC_CHUNKS) c = 3;                                  // tests: tiny chunks on small shapes
+        p.C = (int)(c < 1 ? 1 : (c > (size_t)Bv ? (size_t)Bv : c));
+        p.sync = 1;
+    }
     PartLayout pl = part_layout(M, Nq);
     p.G = pl.G; p.S = pl.S;
     p.nq_pad = nq_padded(Nq);
