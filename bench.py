@@ -218,6 +218,7 @@ def run_triad(args, cfg_key):
     sets = make_device_inputs(cfg, Bl, 1234 + rank, dev, n_sets)
     in_bytes = sum(t.numel() * t.element_size() for t in sets[0][:2])
     model = triad_b200.TriadHotPath(temperature=1.5).to(dev)
+    model.triad_regularizers = False       # BASELINE.json's metric: max-mean similarity + InfoNCE, fwd + bwd
     T = model.temperature
     tokens_local = int(sets[0][2].sum().item()) if cfg["masked"] else Bl * cfg["Nq"]
     fwd_ev = []

@@ -131,6 +131,20 @@ int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float
                       void* dq, void* dv, int dv_f32, float* dT,
                       void* ws, size_t ws_bytes, int flags, void* stream);
 
+/* ---- dense regulariser ----------------------------------------------- */
+/* Elementwise stage of the "non-negative pressure" term, model.py:411-412 (lo = -60) and :525-526
+ * (lo = -20):  l_nonneg = mean(clamp(S, lo, 0)^2) over ALL Bq*Bv*Nq*Nv token pairs, S = T*<q,v>.
+ * `S` holds one chunk of RAW dot products <q,v> ([n] contiguous, `dtype`: the output of a
+ * library GEMM of q rows against a block of patches).  The call
+ *   sums[0] += sum clamp(round(T*raw), lo, 0)^2
+ *   sums[1] += sum coef*clamp'(.)*raw            (this chunk's share of dL/dT)
+ * and, when write_grad != 0, overwrites every element with dL/d(raw) =
+ * coef * clamp(S,lo,0) * [S >= lo] * T in `dtype` (coef = 2*weight/numel chosen by the caller),
+ * which the caller feeds to the two backward GEMMs (dQ += N V, dV = N^T Q).  Deterministic. */
+size_t triad_nonneg_workspace_bytes(void);
+int triad_nonneg_chunk(void* S, size_t n, int dtype, const float* temperature, float lo, float coef,
+                       int write_grad, double* sums, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- retrieval: one query against a gallery, top-k ---------------------------------- */
 /* Replaces the per-pair aggregators retrieval.py:106-110 / :190-193 (direction 0:
  * mean_q max_p) and :112-115 / :195-198 (direction 1: mean_p max_q) and the python double

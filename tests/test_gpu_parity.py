@@ -18,10 +18,13 @@ pytestmark = pytest.mark.gpu
 FWD_SIMT, FWD_1CTA, FWD_SYNC = 1, 2, 8
 
 
-def _model(T, flags=0):
+def _model(T, flags=0, regularizers=False):
+    """regularizers=False: the fused contrastive path on its own (what most tests pin); True: the full loss."""
     import triad_b200
-    m = triad_b200.TriadHotPath(temperature=T).cuda()
+    # the two patch_sparsity_* values are the ones oracle/gen_golden.py gave the reference's methods
+    m = triad_b200.TriadHotPath(temperature=T, patch_sparsity_threshold=0.80, patch_sparsity_weight=0.01).cuda()
     m.triad_fwd_flags = flags
+    m.triad_regularizers = regularizers
     return m
 
 
@@ -109,6 +112,61 @@ def _near_tie_report(q, v, T, idx_a, idx_b):
         x, y = s[idx_a[i, j, a]].item(), s[idx_b[i, j, a]].item()
         worst = max(worst, abs(x - y) / max(abs(x), 1e-30))
     return len(bad), worst
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+@pytest.mark.parametrize("chunk_bytes", [None, 1 << 14])
+def test_golden_total_loss_with_regularisers(case, chunk_bytes, monkeypatch):
+    """total loss, regulariser values and the gradients of the TOTAL loss (dense
+    non-negative pressure + positive-pair terms on top of the contrastive part) vs the reference."""
+    from triad_b200 import regularizers as R
+    if chunk_bytes is not None:                       # many small image chunks: exercises the chunk loop
+        monkeypatch.setattr(R, "CHUNK_BYTES", chunk_bytes)
+    gold = load_golden(case.name)
+    q, v, mask, T = build_inputs(case)
+    m = _model(T, regularizers=True)
+    qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    if case.kind == "av":
+        clip, tok = m.compute_all_similarities_av(qd, vd)
+        total, con, reg, smooth, stats = m.compute_contrastive_loss_av(clip, tok)
+        assert abs(smooth.item() - float(gold["smooth"])) <= 1e-2 * abs(float(gold["smooth"])) + 1e-9
+    else:
+        clip, tok = m.compute_all_similarities_tv(qd, vd, mask.cuda())
+        total, stats = m.compute_contrastive_loss_tv(clip, tok)
+        con = m._contrastive(clip, tok, "tv")[0]
+        reg = total - con
+    fp32 = case.dtype == "fp32"
+    tol = 1e-4 if fp32 else 1e-2
+    assert abs(total.item() - float(gold["total"])) <= tol * abs(float(gold["total"]))
+    assert abs(reg.item() - float(gold["reg"])) <= tol * abs(float(gold["reg"])) + (1e-7 if fp32 else 1e-5)
+    total.backward()
+    P = projection(case)
+    dq = qd.grad.double().cpu() @ P if P is not None else qd.grad.double().cpu()
+    dv = vd.grad.double().cpu() @ P if P is not None else vd.grad.double().cpu()
+    assert rel_err(dq, gold["dq_total"]) < tol
+    assert rel_err(dv, gold["dv_total"]) < tol
+    # dT is a cancelling sum (sum_ij g*clip/T): tolerance relative to the sum of magnitudes, as in test_golden_parity
+    oracle = O.contrastive_step_closed_form(q, v, T, mask)
+    scale = (oracle["g"].abs() * oracle["clip"].abs().double()).sum().item() / T
+    assert abs(m.temperature.grad.item() - float(gold["dT_total"])) < (1e-4 if fp32 else 2e-2) * scale
+    # the regularisers alone: the dense part must be right on its own, not just hidden under the (much
+    # larger) contrastive gradient.  Reference for this check: fp64 autograd of the oracle's restatement
+    # (pinned to the reference's `reg` by tests/test_oracle_golden.py) on the same inputs.
+    q64, v64 = q.double().requires_grad_(), v.double().requires_grad_()
+    T64 = torch.tensor(float(T), dtype=torch.float64, requires_grad=True)
+    tok64 = torch.einsum("iad,jpd->ijap", q64, v64) * T64
+    reg64 = O.regularization_av(tok64, T64)[0] if case.kind == "av" else O.regularization_tv(tok64, 0.80, 0.01)
+    reg64.backward()
+    qd.grad = vd.grad = m.temperature.grad = None
+    clip2, tok2 = (m.compute_all_similarities_av(qd, vd) if case.kind == "av"
+                   else m.compute_all_similarities_tv(qd, vd, mask.cuda()))
+    reg2 = (m.compute_regularization_losses_av(tok2)[0] if case.kind == "av" else m.compute_regularization_losses_tv(tok2))
+    reg2.backward()
+    rtol = 1e-4 if fp32 else 1e-2
+    assert abs(reg2.item() - reg64.item()) <= rtol * abs(reg64.item())
+    assert rel_err(qd.grad.double().cpu(), q64.grad) < rtol
+    assert rel_err(vd.grad.double().cpu(), v64.grad) < rtol
+    assert abs(m.temperature.grad.item() - T64.grad.item()) <= rtol * abs(T64.grad.item()) + 1e-9
 
 
 @pytest.mark.parametrize("flags", [0, FWD_1CTA, FWD_SYNC, FWD_SYNC | FWD_1CTA])

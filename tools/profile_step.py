@@ -20,6 +20,7 @@ def main():
     (q, v, mask), = bench.make_device_inputs(cfg, cfg["B"], 1234, dev, 1)
     q.requires_grad_(True); v.requires_grad_(True)
     m = triad_b200.TriadHotPath(1.5).to(dev)
+    m.triad_regularizers = False
     for _ in range(steps):
         q.grad = v.grad = None
         if mask is None:

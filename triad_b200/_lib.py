@@ -38,6 +38,9 @@ SIGNATURES = {
     "triad_maxmean_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "triad_nonneg_workspace_bytes": (c_size_t, []),
+    "triad_nonneg_chunk": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_float, c_float, c_int, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
     "triad_retrieve_workspace_bytes": (c_size_t, [c_int] * 5),
     "triad_retrieve_scores": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                       c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -1,0 +1,151 @@
+// Dense "non-negative pressure" regulariser of the reference's loss:
+//
+//   l_nonneg = mean over ALL (query token, patch) pairs of clamp(S, lo, 0)^2,   S = T * <q, v>
+//   (src/model.py:411-412 with lo = -60 for audio-visual, :525-526 with lo = -20 for text-visual;
+//    padded text tokens and zero-padded patches take part, exactly as in the reference.)
+//
+// Unlike the max-mean path its gradient dL/dS = 2/numel * clamp(S,lo,0) * [lo <= S <= 0] is DENSE
+// (about half of all pairs), so the backward is two real GEMMs.  With D = 512 a fused
+// flash-attention-style kernel needs the 128 x 512 fp32 dQ (or dV) accumulator = all 512 TMEM
+// columns, leaving none for the recomputed S tile; splitting D doubles the S recompute (6 GEMM
+// units).  Going through HBM with a bf16 S chunk costs 4 bytes per 1024 flops, so the path is:
+// library GEMM (S chunk) -> THIS kernel (in place: S -> dL/d<q,v>, plus the two reductions)
+// -> two library GEMMs (dQ += N V, dV = N^T Q), 3 GEMM units in total.  See DESIGN.md §4 K5.
+//
+// The kernel is a pure HBM stream: one 16-byte load and one 16-byte store per 8 (bf16) or 4
+// (fp32) pairs, fp64 block partials reduced in a fixed order by a second launch (deterministic).
+#include "common.cuh"
+
+namespace triad {
+namespace dense {
+
+constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 148 * 8;
+
+template <typename T> struct Pack;
+template <> struct Pack<__nv_bfloat16> {
+    static constexpr int kElems = 8;
+    __device__ static __forceinline__ void load(const void* p, float (&f)[8]) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = __uint_as_float(w[k] << 16);
+            f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+    }
+    __device__ static __forceinline__ void store(void* p, const float (&f)[8]) {
+        uint4 u;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+            w[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+    // the reference's token_sims element: bf16(bf16 GEMM output * fp32 T)  (model.py:387 under autocast)
+    __device__ static __forceinline__ float scaled(float raw, float Tv) { return __bfloat162float(__float2bfloat16_rn(raw * Tv)); }
+    __device__ static __forceinline__ float scalar(const void* p) { return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)); }
+    __device__ static __forceinline__ void put(void* p, float x) { *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(x); }
+};
+template <> struct Pack<float> {
+    static constexpr int kElems = 4;
+    __device__ static __forceinline__ void load(const void* p, float (&f)[4]) {
+        const float4 u = *reinterpret_cast<const float4*>(p);
+        f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+    }
+    __device__ static __forceinline__ void store(void* p, const float (&f)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+    __device__ static __forceinline__ float scaled(float raw, float Tv) { return raw * Tv; }
+    __device__ static __forceinline__ float scalar(const void* p) { return *reinterpret_cast<const float*>(p); }
+    __device__ static __forceinline__ void put(void* p, float x) { *reinterpret_cast<float*>(p) = x; }
+};
+
+// one element: accumulates clamp^2 and dS*raw, returns dL/d(raw) = coef * clamp(S,lo,0) * [S >= lo] * T
+__device__ __forceinline__ float one(float raw, float Tv, float lo, float coefT, float coef, double& s2, double& sT,
+                                     float s /* = scaled(raw) */) {
+    const float n = fminf(fmaxf(s, lo), 0.f);
+    s2 += (double)n * (double)n;
+    const float pass = (s >= lo) ? n : 0.f;          // clamp's gradient is 1 on [lo, 0] (n == 0 beyond 0 anyway)
+    sT += (double)(coef * pass) * (double)raw;       // dS/dT = <q,v> = raw
+    return coefT * pass;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+nonneg_kernel(void* __restrict__ S, size_t n, const float* __restrict__ Tptr, float lo, float coef, int write_grad,
+              double* __restrict__ partials) {
+    constexpr int E = Pack<T>::kElems;
+    const float Tv = *Tptr;
+    const float coefT = coef * Tv;
+    double s2 = 0.0, sT = 0.0;
+    char* base = reinterpret_cast<char*>(S);
+    const size_t nvec = n / E;
+    for (size_t k = (size_t)blockIdx.x * kThreads + threadIdx.x; k < nvec; k += (size_t)gridDim.x * kThreads) {
+        float f[E], o[E];
+        Pack<T>::load(base + k * E * sizeof(T), f);
+#pragma unroll
+        for (int c = 0; c < E; ++c) o[c] = one(f[c], Tv, lo, coefT, coef, s2, sT, Pack<T>::scaled(f[c], Tv));
+        if (write_grad) Pack<T>::store(base + k * E * sizeof(T), o);
+    }
+    // tail (n % E elements), handled by block 0
+    if (blockIdx.x == 0) {
+        for (size_t k = nvec * E + threadIdx.x; k < n; k += kThreads) {
+            const float raw = Pack<T>::scalar(base + k * sizeof(T));
+            const float o = one(raw, Tv, lo, coefT, coef, s2, sT, Pack<T>::scaled(raw, Tv));
+            if (write_grad) Pack<T>::put(base + k * sizeof(T), o);
+        }
+    }
+    __shared__ double r2[kThreads / 32], rT[kThreads / 32];
+    s2 = warp_sum_d(s2);
+    sT = warp_sum_d(sT);
+    if ((threadIdx.x & 31) == 0) { r2[threadIdx.x >> 5] = s2; rT[threadIdx.x >> 5] = sT; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kThreads / 32; ++w) { a += r2[w]; b += rT[w]; }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// sums[0] += sum clamp^2 ; sums[1] += sum dS * <q,v>   (fixed order over the block partials)
+__global__ void nonneg_finish_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums) {
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < nblocks; k += 32) { a += partials[2 * k]; b += partials[2 * k + 1]; }
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    if (threadIdx.x == 0) { sums[0] += a; sums[1] += b; }
+}
+
+}  // namespace dense
+}  // namespace triad
+
+using namespace triad;
+
+extern "C" size_t triad_nonneg_workspace_bytes(void) { return (size_t)dense::kMaxBlocks * 2 * sizeof(double); }
+
+extern "C" int triad_nonneg_chunk(void* S, size_t n, int dtype, const float* temperature, float lo, float coef,
+                                  int write_grad, double* sums, void* ws, size_t ws_bytes, void* stream) {
+    if (!S || !temperature || !sums || !ws) return fail_msg(TRIAD_ERR_BAD_ARG, "nonneg_chunk: null pointer");
+    if (dtype != TRIAD_DTYPE_F32 && dtype != TRIAD_DTYPE_BF16) return fail_msg(TRIAD_ERR_BAD_ARG, "nonneg_chunk: dtype");
+    if (n == 0) return fail_msg(TRIAD_ERR_BAD_SHAPE, "nonneg_chunk: empty chunk");
+    if (!(lo < 0.f)) return fail_msg(TRIAD_ERR_BAD_ARG, "nonneg_chunk: lo must be negative");
+    if ((uintptr_t)S & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "nonneg_chunk: S must be 16-byte aligned");
+    if (ws_bytes < triad_nonneg_workspace_bytes()) return fail_msg(TRIAD_ERR_WORKSPACE, "nonneg_chunk: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int E = dtype == TRIAD_DTYPE_BF16 ? 8 : 4;
+    size_t want = (n / E + dense::kThreads - 1) / dense::kThreads;
+    int blocks = (int)(want < 1 ? 1 : (want > (size_t)dense::kMaxBlocks ? (size_t)dense::kMaxBlocks : want));
+    double* partials = (double*)ws;
+    if (dtype == TRIAD_DTYPE_BF16)
+        dense::nonneg_kernel<__nv_bfloat16><<<blocks, dense::kThreads, 0, st>>>(S, n, temperature, lo, coef, write_grad, partials);
+    else
+        dense::nonneg_kernel<float><<<blocks, dense::kThreads, 0, st>>>(S, n, temperature, lo, coef, write_grad, partials);
+    TRIAD_LAUNCH_CHECK("nonneg_kernel");
+    dense::nonneg_finish_kernel<<<1, 32, 0, st>>>(partials, blocks, sums);
+    TRIAD_LAUNCH_CHECK("nonneg_finish_kernel");
+    return TRIAD_OK;
+}

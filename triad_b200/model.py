@@ -15,8 +15,9 @@ One deliberate difference: the reference returns the dense ``token_sims`` tensor
 return value is a ``TokenSims`` handle that carries the saved argmax indices and the fp32 clip
 matrix, has the reference tensor's ``.shape`` / ``.dtype`` / ``.device``, and can
 ``.materialize()`` the dense tensor on demand (visualisation, tests, small batches).  The loss
-methods accept that handle (or, for API compatibility, a dense tensor, in which case only the
-contrastive part — which never needed token_sims — is computed from ``clip_sims``).
+methods accept that handle and evaluate the reference's regularisers from the embeddings it
+carries (regularizers.py); given a dense tensor instead, only the contrastive part — which
+never needed token_sims — is computed from ``clip_sims``.
 """
 from __future__ import annotations
 
@@ -133,6 +134,8 @@ class TriadSimilarityMixin:
 
     #: forwarded to triad_maxmean_fwd (tests use it to pin a kernel variant)
     triad_fwd_flags: int = 0
+    #: evaluate the reference's regularisation terms (model.py:394-428, :516-542) in the loss methods
+    triad_regularizers: bool = True
 
     # -- similarities -----------------------------------------------------------------------
     def _similarities(self, q_feats, visual_feats, attention_mask, prefix):
@@ -170,21 +173,49 @@ class TriadSimilarityMixin:
         """20 * relu(-log T)^2 — the l_cal term of model.py:420-427 (a scalar on the parameter)."""
         return 20.0 * torch.clamp(-torch.log(self.temperature), min=0) ** 2
 
+    def _dense_terms_enabled(self, token_sims) -> bool:
+        return bool(getattr(self, "triad_regularizers", True)) and isinstance(token_sims, TokenSims)
+
+    def compute_regularization_losses_av(self, token_sims):
+        """(reg, 0.01*l_smooth) — model.py:410-428: 20*l_cal + 0.15*mean(clamp(S,-60,0)^2) + 0.01*l_smooth."""
+        from . import regularizers as R
+        tok = token_sims
+        l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -60.0)
+        diag = R.positive_pair_token_sims(tok.q, tok.v, self.temperature)
+        l_smooth = R.temporal_smoothness(diag)
+        reg = self._temperature_calibration() + 0.15 * l_nonneg + 0.01 * l_smooth
+        return reg, 0.01 * l_smooth
+
+    def compute_regularization_losses_tv(self, token_sims):
+        """reg — model.py:516-542: 0.15*mean(clamp(S,-20,0)^2) + patch_sparsity_weight*sparsity."""
+        from . import regularizers as R
+        tok = token_sims
+        l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -20.0)
+        diag = R.positive_pair_token_sims(tok.q, tok.v, self.temperature)
+        sparsity = R.patch_sparsity(diag, self.patch_sparsity_threshold)
+        return 0.15 * l_nonneg + self.patch_sparsity_weight * sparsity
+
     def compute_contrastive_loss_av(self, clip_sims, token_sims):
         """(total, contrastive, reg, 0.01*l_smooth, stats) — model.py:430-472.
 
-        The dense regularisers (0.15*mean(clamp(S,-60,0)^2) and the temporal smoothness term)
-        read the full token-similarity tensor; they are the SURVEY §8(f1) follow-up and are not
-        part of this build's fused path: ``reg`` carries the temperature-calibration term only and
-        the returned smoothness term is zero.  See DESIGN.md §"Out of scope"."""
+        ``token_sims`` is the TokenSims handle of compute_all_similarities_av; the regularisers are
+        evaluated from the embeddings it carries (regularizers.py).  With ``self.triad_regularizers =
+        False`` (or a dense tensor in place of the handle) only the contrastive loss and the scalar
+        temperature-calibration term are computed — the fused max-mean + InfoNCE path on its own, which
+        is what BASELINE.json's metric times."""
         contrastive, stats = self._contrastive(clip_sims, token_sims, "av")
-        reg = self._temperature_calibration()
-        smooth = torch.zeros((), dtype=torch.float32, device=contrastive.device)
+        if self._dense_terms_enabled(token_sims):
+            reg, smooth = self.compute_regularization_losses_av(token_sims)
+        else:
+            reg = self._temperature_calibration()
+            smooth = torch.zeros((), dtype=torch.float32, device=contrastive.device)
         return contrastive + reg, contrastive, reg, smooth, stats
 
     def compute_contrastive_loss_tv(self, clip_sims, token_sims):
-        """(total, stats) — model.py:544-593 (contrastive part; see compute_contrastive_loss_av)."""
+        """(total, stats) — model.py:544-593 (see compute_contrastive_loss_av for the regulariser switch)."""
         contrastive, stats = self._contrastive(clip_sims, token_sims, "tv")
+        if self._dense_terms_enabled(token_sims):
+            return contrastive + self.compute_regularization_losses_tv(token_sims), stats
         return contrastive, stats
 
     # -- per-pair normalised similarity (viz / forward()) -------------------------------------
