@@ -38,8 +38,6 @@ CONFIGS = {
     "cfg4": dict(B=8192, Nq=250, Nv=256, D=512, masked=False,
                  name="cfg4: B=8192 global, 250 x 256, D=512, bf16 fwd+bwd, rows sharded over ranks"),
 }
-KERNELS_PER_STEP = 11    # row_scale, maxmean_tc, finalize_clip, nce_partial, nce_combine x2, nce_finish,
-                         # nce_final_reduce, dq_gather, dv_scatter, dT
 
 
 def algorithmic_flops(B_rows, B_cols, n_tokens_total, Nv, D):
@@ -198,7 +196,7 @@ def run_triad(args, cfg_key):
     import torch.distributed as dist
     import triad_b200
     from triad_b200 import _lib
-    from triad_b200.dist import sharded_contrastive_step
+    from triad_b200.dist import CudaKernels, sharded_contrastive_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,8 +239,24 @@ def run_triad(args, cfg_key):
         total.backward()
         return total
 
+    class TimedKernels(CudaKernels):
+        """The product kernels, with CUDA events around the forward call (for the roofline entry)."""
+        record = False
+
+        def maxmean_fwd(self, q, v, scale, T_):
+            if not self.record:
+                return super().maxmean_fwd(q, v, scale, T_)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = super().maxmean_fwd(q, v, scale, T_)
+            e1.record(); fwd_ev.append((e0, e1))
+            return out
+
+    timed_kernels = TimedKernels()
+
     def step_sharded(q, v, mask, record=False):
-        out = sharded_contrastive_step(q, v, T, mask)
+        timed_kernels.record = record
+        out = sharded_contrastive_step(q, v, T, mask, kernels=timed_kernels)
         return out["loss"]
 
     step = step_single if world == 1 else step_sharded
@@ -271,8 +285,10 @@ def run_triad(args, cfg_key):
     # ---- device-resident arm -------------------------------------------------------------------
     for i in range(args.warmup):
         step(*sets[i % n_sets])
+    launches0 = lib.triad_launch_count()
     with ClockSampler(local) as clocks:
         ms = timed(lambda i: step(*sets[i % n_sets], record=True), args.steps)
+    gpu_launches = int(lib.triad_launch_count() - launches0)     # libtriad_b200.so kernels inside the timed region (this rank)
     value = float(B) * B / (ms * 1e-3)
 
     # ---- end-to-end arm: pinned host inputs -> H2D -> step -> loss D2H --------------------------
@@ -329,6 +345,20 @@ def run_triad(args, cfg_key):
     e2e_ms = e2e_t.item()
     h2d = in_bytes + (host[0][2].numel() * 8 if host[0][2] is not None else 0)
 
+    # ---- the reference's FULL loss (contrastive + regularisers), reported beside the metric ----
+    full = None
+    if world == 1:
+        model.triad_regularizers = True
+        for i in range(2):
+            step(*sets[i % n_sets])
+        k_full = max(3, min(args.steps, 10))
+        full_ms = timed(lambda i: step(*sets[i % n_sets]), k_full)
+        model.triad_regularizers = False
+        full = {"value": float(B) * B / (full_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": full_ms, "steps": k_full,
+                "what": "same step with the reference's regularisers on (model.py:394-428 / :516-542): dense non-negative "
+                        "pressure through 3 library GEMMs per image chunk + triad_nonneg_chunk, smoothness / sparsity on "
+                        "the positive pairs; not part of BASELINE.json's metric"}
+
     # ---- roofline of the dominant kernel (tcgen05 forward) ---------------------------------------
     peak, peak_sustained, peak_src = measured_peaks()
     roof = None
@@ -360,9 +390,11 @@ def run_triad(args, cfg_key):
             "clocks": clocks.summary(),
             "e2e": {"value": float(B) * B / (e2e_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h["bytes"]},
-            "gpu_launches": (KERNELS_PER_STEP if world == 1 else KERNELS_PER_STEP - 1) * args.steps,
+            "gpu_launches": gpu_launches,
             "roofline": roof,
         }
+        if full is not None:
+            out["full_loss"] = full
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_seconds)
         print(json.dumps(out), flush=True)

@@ -59,6 +59,9 @@ int         triad_abi_version(void);
 const char* triad_status_string(int status);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
 const char* triad_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (all threads); lets a
+ * caller state exactly how many of the library's kernels ran inside a timed region. */
+long long   triad_launch_count(void);
 /* 0 if `device` can run the kernels (compute capability 10.x), TRIAD_ERR_ARCH otherwise. */
 int         triad_device_check(int device);
 

@@ -22,6 +22,7 @@ SIGNATURES = {
     "triad_abi_version": (c_int, []),
     "triad_status_string": (c_char_p, [c_int]),
     "triad_last_error": (c_char_p, []),
+    "triad_launch_count": (ctypes.c_longlong, []),
     "triad_device_check": (c_int, [c_int]),
     "triad_row_scale": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "triad_maxmean_fwd_workspace_bytes": (c_size_t, [c_int] * 6),

@@ -3,9 +3,14 @@
 
 #include <string.h>
 
+#include <atomic>
+
 namespace triad {
 
 static thread_local char g_last_error[256] = "";
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* where) {
     snprintf(g_last_error, sizeof g_last_error, "%s: %s", where, cudaGetErrorString(e));
@@ -44,6 +49,8 @@ extern "C" const char* triad_status_string(int s) {
 }
 
 extern "C" const char* triad_last_error(void) { return g_last_error; }
+
+extern "C" long long triad_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int triad_device_check(int device) {
     int major = 0;

@@ -19,10 +19,13 @@ int fail_msg(int status, const char* msg);
         if (e__ != cudaSuccess) return ::triad::cuda_fail(e__, #expr);      \
     } while (0)
 
+void count_launch();                                // triad_launch_count(): kernels launched by this library
+
 #define TRIAD_LAUNCH_CHECK(what)                                            \
     do {                                                                    \
         cudaError_t e__ = cudaGetLastError();                               \
         if (e__ != cudaSuccess) return ::triad::cuda_fail(e__, what);       \
+        ::triad::count_launch();                                            \
     } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -361,9 +361,111 @@ dv_gather_kernel(const T* __restrict__ q, const DvEntry* __restrict__ entries, c
             float prev[E];
             LoadAs<OutT, E>::get(dst, prev);
 #pragma unroll
-            for (int c = 0; c < E; ++c) o[c] += prev[c];
+            for (int c = 0; c < E; ++c) o[c] = __fmaf_rn(acc[c], Tval, prev[c]);    // explicit: both gather kernels round alike
         }
         StoreAs<OutT, E>::put(dst, o);
+    }
+}
+
+// bf16 specialisation of the gather above, shaped for the two things ncu shows it short of — bytes in
+// flight (the generic kernel's 102 registers allow 16 warps/SM; L2 throughput sits at 44 %) and issue
+// slots (54 % busy, mostly bf16 unpacking and scalar FMAs):
+//   * rows stay PACKED (one uint4 per lane and row) until they are consumed, so kU rows in flight cost
+//     4*kU registers instead of 8*kU and kMinBlocks CTAs fit per SM;
+//   * FFMA2 (two fp32 FMAs per issue slot) on the (lo,hi) halves of every 32-bit word;
+//   * the byte offset of the row is computed once per entry, before the broadcast.
+// Same summation order as the generic kernel (entries in list order, fp32), so the results are
+// bit-identical to it.
+__device__ __forceinline__ void ffma2_pair(float2& acc, float w, uint32_t pair) {
+    float2 wv = make_float2(w, w);
+    float2 vv = make_float2(__uint_as_float(pair << 16), __uint_as_float(pair & 0xffff0000u));
+    unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc);
+    const unsigned long long b = *reinterpret_cast<unsigned long long*>(&wv);
+    const unsigned long long c = *reinterpret_cast<unsigned long long*>(&vv);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(b), "l"(c));
+    acc = *reinterpret_cast<float2*>(&a);
+}
+
+// kW = 16-byte chunks per lane and row: kW = 1 -> a warp covers 512 bytes of the row (D = 512: two warps per
+// segment, each walking the entry list); kW = 2 -> one warp covers 1 KB with two loads per row, halving the
+// list/shuffle overhead per byte.
+template <typename OutT, int kU, int kW, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
+dv_gather_bf16_kernel(const __nv_bfloat16* __restrict__ q, const DvEntry* __restrict__ entries,
+                      const uint32_t* __restrict__ seg, const float* __restrict__ Tptr, int j0, int nj, int Nv, int D,
+                      int wps, size_t Mrows, int accumulate, OutT* __restrict__ dv) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 8 + warp;
+    const long long sid = wid / wps;
+    const int ch0 = (int)(wid - sid * wps) * 32 * kW + lane;    // this lane's first 16-byte chunk; the others follow at +32
+    if (sid >= (long long)nj * Nv) return;
+    const int jl = (int)(sid / Nv), p = (int)(sid % Nv);
+    const uint32_t e0 = seg[(size_t)jl * (Nv + 1) + p], e1 = seg[(size_t)jl * (Nv + 1) + p + 1];
+    const DvEntry* list = entries + (size_t)jl * Mrows;
+    // 32-bit byte offsets from the (uniform) block base: a query block is <= 64 MB (dv_plan), so the
+    // address is one register per row in flight instead of two
+    const char* qbase = reinterpret_cast<const char*>(q);
+    const uint32_t row_bytes = (uint32_t)D * 2u;
+    bool act[kW];
+    uint32_t lane_off[kW];
+#pragma unroll
+    for (int k = 0; k < kW; ++k) { act[k] = (ch0 + 32 * k) * 8 < D; lane_off[k] = act[k] ? (uint32_t)(ch0 + 32 * k) * 16u : 0u; }
+
+    float2 acc[kW][4];
+#pragma unroll
+    for (int k = 0; k < kW; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[k][c] = make_float2(0.f, 0.f);
+
+    DvEntry next; next.row = 0; next.w = 0.f;
+    if (e0 + lane < e1) next = list[e0 + lane];
+    for (uint32_t base = e0; base < e1; base += 32) {
+        const uint32_t my_row = next.row;
+        const float my_w = next.w;
+        next.row = 0; next.w = 0.f;
+        if (base + 32 + lane < e1) next = list[base + 32 + lane];
+        const int n = min(32u, e1 - base);
+        for (int l = 0; l < n; l += kU) {
+            uint4 d[kU][kW];
+            float w[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                // slots past n re-read the segment's last entry with weight 0: no branch in the batch
+                const int src = min(l + u, n - 1);
+                const uint32_t row = __shfl_sync(0xffffffffu, my_row, src);
+                const float ww = __shfl_sync(0xffffffffu, my_w, src);
+                w[u] = (l + u < n) ? ww : 0.f;
+#pragma unroll
+                for (int k = 0; k < kW; ++k)
+                    d[u][k] = __ldg(reinterpret_cast<const uint4*>(qbase + (row * row_bytes + lane_off[k])));
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int k = 0; k < kW; ++k) {
+                    ffma2_pair(acc[k][0], w[u], d[u][k].x); ffma2_pair(acc[k][1], w[u], d[u][k].y);
+                    ffma2_pair(acc[k][2], w[u], d[u][k].z); ffma2_pair(acc[k][3], w[u], d[u][k].w);
+                }
+        }
+    }
+    const float Tval = *Tptr;
+#pragma unroll
+    for (int k = 0; k < kW; ++k) {
+        if (!act[k]) continue;
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { o[2 * c] = acc[k][c].x * Tval; o[2 * c + 1] = acc[k][c].y * Tval; }
+        OutT* dst = dv + ((size_t)(j0 + jl) * Nv + p) * D + (ch0 + 32 * k) * 8;
+        if (accumulate) {                       // later query blocks add to the fp32 partial of the earlier ones
+            float prev[8];
+            LoadAs<OutT, 8>::get(dst, prev);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                o[2 * c] = __fmaf_rn(acc[k][c].x, Tval, prev[2 * c]);
+                o[2 * c + 1] = __fmaf_rn(acc[k][c].y, Tval, prev[2 * c + 1]);
+            }
+        }
+        StoreAs<OutT, 8>::put(dst, o);
     }
 }
 
@@ -493,6 +595,28 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
                 dv_scatter_sort_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(
                     idx_b, g_b, rs_b, start, img_pitch, j0, nj, nq, Bv, Nq, Nv, nq_pad, Mb, entries);
                 TRIAD_LAUNCH_CHECK("dv_scatter_sort_kernel");
+                if constexpr (sizeof(T) == 2) {
+                    if (!(bwd_flags & TRIAD_BWD_GENERIC_DV)) {
+                        const __nv_bfloat16* qb16 = (const __nv_bfloat16*)q_b;
+                        // rows of more than 512 bytes: one warp per segment, two 16-byte loads per lane and row
+                        // (measured at cfg 2: 1.46 -> 1.36 ms for the whole dv pass); otherwise one load per lane
+                        const bool wide_rows = D > 256;
+#define TRIAD_DVG_K(OUT, DST, J0, U, W, MB) do { \
+                            const int wps_ = ceil_div(D / 8, 32 * W); \
+                            const unsigned grid_ = (unsigned)(((long long)nj * Nv * wps_ + 7) / 8); \
+                            dv_gather_bf16_kernel<OUT, U, W, MB><<<grid_, 256, 0, st>>>(qb16, entries, seg, Tp, J0, nj, Nv, D, wps_, Mb, b > 0, DST); \
+                        } while (0)
+#define TRIAD_DVG(OUT, DST, J0) \
+                        if (wide_rows) TRIAD_DVG_K(OUT, DST, J0, 4, 2, 3); else TRIAD_DVG_K(OUT, DST, J0, 8, 1, 3);
+                        if (pl.scratch) { TRIAD_DVG(float, scratch, 0) }
+                        else if (out_f32) { TRIAD_DVG(float, (float*)dv, j0) }
+                        else { TRIAD_DVG(__nv_bfloat16, (__nv_bfloat16*)dv, j0) }
+#undef TRIAD_DVG
+#undef TRIAD_DVG_K
+                        TRIAD_LAUNCH_CHECK("dv_gather_bf16_kernel");
+                        continue;
+                    }
+                }
                 if (pl.scratch)          // accumulate this image batch in fp32 scratch (local image index), convert at the end
                     dv_gather_kernel<T, float><<<ggrid, 256, 0, st>>>(q_b, entries, seg, Tp, 0, nj, Nv, D, wps, Mb, b > 0, scratch);
                 else if (out_f32)

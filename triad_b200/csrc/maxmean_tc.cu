@@ -463,6 +463,7 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mv, p));
+    count_launch();
     return TRIAD_OK;
 }
 
