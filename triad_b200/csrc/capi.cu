@@ -90,7 +90,10 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
     const bool use_tc = dtype == TRIAD_DTYPE_BF16 && !(flags & TRIAD_FWD_FORCE_SIMT) && tc_supported(Nv, D);
     int rc;
     if (use_tc) {
-        const int cta_group = (flags & TRIAD_FWD_FORCE_1CTA) ? 1 : 2;
+        // A single row tile of <= 128 tokens (one text query against a gallery): cta_group::1 — a pair would
+        // spend a 256-row MMA on <= 128 rows, and at one tile per image that MMA time equals the HBM time of
+        // the image, leaving no slack to overlap; alone, each SM streams its own images at twice that rate.
+        const int cta_group = ((flags & TRIAD_FWD_FORCE_1CTA) || M <= 128) ? 1 : 2;
         rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags, st);
     } else {
         rc = launch_maxmean_simt(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, dtype, part, idx, st);

@@ -492,17 +492,28 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     p.idx16 = Nv > 256;
     p.num_kb = D / kBlockK;
     p.n_m = n_m;
-    // image chunk: keep all of V L2-resident when it is small; up to ~96 MB (cfg 2: 67 MB) the clusters may be
-    // anywhere in V (it still fits the 126 MB L2); beyond that every cluster walks the same ~32 MB chunk.
-    const size_t v_bytes = (size_t)Bv * Nv * D * 2;
+    // Tile order (TileIter).  V small: any order, V stays in L2 (up to ~96 MB — cfg 2 is 67 MB — the clusters
+    // may be anywhere in V).  V larger than L2: if there are enough query tiles to give every cluster a few
+    // items per ~32 MB image chunk, all clusters walk the same chunk at the same time (V is read from HBM once);
+    // otherwise (retrieval: one or a few query tiles against a huge gallery) each cluster keeps to its own
+    // images and runs all query tiles against a handful of them back to back, so the re-reads hit L2.
+    const size_t img_bytes = (size_t)Nv * D * 2;
+    const size_t v_bytes = (size_t)Bv * img_bytes;
+    int n_clusters = sms / cta_group;
     p.C = (v_bytes <= (size_t)48 << 20) ? Bv : (Bv < 64 ? Bv : 64);
     p.sync = 0;
-    if (v_bytes > (size_t)96 << 20 || (flags & TRIAD_FWD_SYNC_CHUNKS)) {
-        size_t c = ((size_t)32 << 20) / ((size_t)Nv * D * 2);
-        if (flags & TRIAD_FWD_SYNC_CHUNKS) c = 3;                                  // tests: tiny chunks on small shapes
-        p.C = (int)(c < 1 ? 1 : (c > (size_t)Bv ? (size_t)Bv : c));
-        p.sync = 1;
+    if (v_bytes > (size_t)96 << 20) {
+        size_t c32 = ((size_t)32 << 20) / img_bytes;
+        if (c32 < 1) c32 = 1;
+        if ((size_t)n_m * c32 >= (size_t)4 * n_clusters) {
+            p.C = (int)(c32 > (size_t)Bv ? (size_t)Bv : c32);
+            p.sync = 1;
+        } else {
+            size_t c = ((size_t)48 << 20) / ((size_t)n_clusters * img_bytes);
+            p.C = (int)(c < 1 ? 1 : (c > 64 ? 64 : c));
+        }
     }
+    if (flags & TRIAD_FWD_SYNC_CHUNKS) { p.C = Bv < 3 ? Bv : 3; p.sync = 1; }     // tests: tiny chunks on small shapes
     PartLayout pl = part_layout(M, Nq);
     p.G = pl.G; p.S = pl.S;
     p.nq_pad = nq_padded(Nq);
@@ -525,7 +536,6 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
         if (rc) return rc;
     }
     const long long total = (long long)n_m * Bv;
-    int n_clusters = sms / cta_group;
     if ((long long)n_clusters > total) n_clusters = (int)total;
     if (n_clusters < 1) n_clusters = 1;
     if (n_sub > 1) return cta_group == 2 ? launch_t<2, true>(mq, mv, p, n_clusters, st) : launch_t<1, true>(mq, mv, p, n_clusters, st);

@@ -31,8 +31,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive on a (possibly remote) CTA's barrier.  Default semantics (.release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive: what crosses this barrier is TENSOR memory, ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync, not global/shared data — the explicit .release.cluster form makes
+// ptxas emit MEMBAR.ALL.GPU + ERRBAR per arrive (once per tile and epilogue warp), which stalls the hand-back
+// of the accumulator until the warp's outstanding global stores have drained.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
