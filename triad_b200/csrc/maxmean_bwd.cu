@@ -297,6 +297,131 @@ dv_scatter_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g
 }
 
 // ---------------------------------------------------------------------------------------
+// dv step 1, grouped variant (bf16 path, Nv <= kGroupMaxNv): NO global count / offset pass.
+//   ncu on the three kernels above at cfg 2: count 120 us + offsets 9 us + scatter 320 us, the scatter
+//   writing 315 MB to DRAM for a 131 MB list (16.4 M lone 8-byte stores, each dirtying its own sector).
+//   Here the rows of a query block are cut into GROUPS of kGroupRows consecutive rows; one CTA sorts one
+//   (image, group) by winning patch entirely in shared memory — every lane loads its 32 winners up front
+//   (independent loads), per-warp histograms, one scan, a stable placement of 16-bit local row numbers —
+//   and writes the group's list as ONE contiguous, fully coalesced run into the group's own region of the
+//   entry buffer.  The per-(image, group) segment table replaces the global offsets; the gather walks a
+//   patch's list group by group.  Order inside a patch is still "rows ascending", so dv is bit-identical to
+//   the ungrouped path.
+// ---------------------------------------------------------------------------------------
+constexpr int kGroupRows = 8192;
+constexpr int kGroupWarps = 8;
+constexpr int kGroupPerLane = kGroupRows / (kGroupWarps * 32);      // 32 rows per lane
+constexpr int kGroupMaxNv = 1024;
+
+static size_t group_sort_smem(int Nv) { return (size_t)kGroupRows * 2 + (size_t)(kGroupWarps + 2) * Nv * 4 + 16; }
+
+template <typename IdxT>
+__global__ void __launch_bounds__(kGroupWarps * 32, 3)
+dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, const float* __restrict__ row_scale,
+                     size_t img_pitch, int j0, int n_groups, int Mb, int Bv, int Nq, int Nv, int nq_pad,
+                     uint32_t* __restrict__ segc, DvEntry* __restrict__ entries) {
+    extern __shared__ __align__(16) unsigned char gs_smem[];
+    uint16_t* sorted = reinterpret_cast<uint16_t*>(gs_smem);                              // [kGroupRows] local row numbers
+    uint32_t* hist = reinterpret_cast<uint32_t*>(gs_smem + (size_t)kGroupRows * 2);       // [warps][Nv]
+    uint32_t* lbase = hist + kGroupWarps * Nv;                                            // [Nv]
+    uint32_t* tot = lbase + Nv;                                                           // [Nv]
+    uint32_t* total_s = tot + Nv;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int jl = blockIdx.x / n_groups, c = blockIdx.x - jl * n_groups;
+    const int j = j0 + jl;
+    const int x_group = c * kGroupRows;
+    const IdxT* base = idx + (size_t)j * img_pitch;
+    const uint32_t lt = (1u << lane) - 1u;
+
+    for (int k = tid; k < kGroupWarps * Nv; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+
+    // ---- 1. every lane fetches its 32 winners (independent loads), then the per-warp histogram.
+    //         Winners are kept packed two per register (0xffff = row absent or zero weight). ----
+    uint32_t pv[kGroupPerLane / 2];
+    uint32_t* myh = hist + warp * Nv;
+    {
+        const int xw = x_group + warp * (kGroupPerLane * 32) + lane;
+        int i = xw / Nq, a = xw - i * Nq;                     // advanced incrementally: +32 rows per step
+#pragma unroll
+        for (int k = 0; k < kGroupPerLane; ++k) {
+            const int x = xw + k * 32;
+            const bool in = x < Mb;                         // two INDEPENDENT loads per row (no load behind a branch)
+            const float rsx = in ? row_scale[x] : 0.f;
+            const uint32_t pp = in ? (uint32_t)base[(size_t)i * nq_pad + a] : 0u;
+            const uint32_t p = (rsx != 0.f) ? pp : 0xffffu;
+            if (k & 1) pv[k >> 1] |= p << 16; else pv[k >> 1] = p;
+            a += 32;
+            while (a >= Nq) { a -= Nq; ++i; }
+        }
+#pragma unroll
+        for (int k = 0; k < kGroupPerLane; ++k) {
+            const uint32_t p = (pv[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+            if (p != 0xffffu) atomicAdd(&myh[p], 1u);
+        }
+    }
+    __syncthreads();
+    // ---- 2. per patch: exclusive prefix over the warps, then an exclusive scan over the patches ----
+    for (int p = tid; p < Nv; p += blockDim.x) {
+        uint32_t run = 0;
+        for (int w = 0; w < kGroupWarps; ++w) { const uint32_t t = hist[w * Nv + p]; hist[w * Nv + p] = run; run += t; }
+        tot[p] = run;
+    }
+    __syncthreads();
+    uint32_t* seg_out = segc + (size_t)blockIdx.x * (Nv + 1);
+    if (warp == 0) {
+        uint32_t carry = 0;
+        for (int p0 = 0; p0 < Nv; p0 += 32) {
+            const int p = p0 + lane;
+            const uint32_t v = (p < Nv) ? tot[p] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (p < Nv) { lbase[p] = carry + incl - v; seg_out[p] = carry + incl - v; }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) { *total_s = carry; seg_out[Nv] = carry; }
+    }
+    __syncthreads();
+    // ---- 3. placement.  Slot = run start + this warp's prefix + a shared-memory atomic counter.  A lane's own
+    //         rows and a warp's successive steps take increasing slots; only rows that meet in the SAME 32-row
+    //         step (or, in principle, reordered atomics) can land out of order, so step 3b sorts every patch's
+    //         run by row — an insertion sort over an almost sorted run of ~Rows/Nv 16-bit values, one thread
+    //         per patch.  (__match_any_sync ranking made this phase 40 % of the kernel: its latency grows with
+    //         the number of distinct keys in the warp, here ~30.) ----
+#pragma unroll
+    for (int k = 0; k < kGroupPerLane; ++k) {
+        const uint32_t pk = (pv[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+        if (pk != 0xffffu) {
+            const uint32_t slot = lbase[pk] + atomicAdd(&myh[pk], 1u);
+            sorted[slot] = (uint16_t)(warp * (kGroupPerLane * 32) + k * 32 + lane);
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < Nv; p += blockDim.x) {
+        const uint32_t b0 = lbase[p], cnt = tot[p];
+        for (uint32_t u = 1; u < cnt; ++u) {
+            const uint16_t key = sorted[b0 + u];
+            uint32_t v = u;
+            while (v > 0 && sorted[b0 + v - 1] > key) { sorted[b0 + v] = sorted[b0 + v - 1]; --v; }
+            sorted[b0 + v] = key;
+        }
+    }
+    __syncthreads();
+    // ---- 4. the group's list leaves as one contiguous run; the weight is attached here ----
+    const uint32_t n = *total_s;
+    DvEntry* out = entries + (size_t)blockIdx.x * kGroupRows;
+#pragma unroll 8
+    for (uint32_t t = tid; t < n; t += kGroupWarps * 32) {
+        const int x = x_group + (int)sorted[t];
+        const int i = x / Nq;
+        DvEntry d; d.row = (uint32_t)x; d.w = row_scale[x] * g[(size_t)i * Bv + j];
+        out[t] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // dv step 2: one warp per (image, patch) segment and 32-chunk column block of D (a 512-byte
 // bf16 column block per warp: D = 512 -> 2 warps per segment); lanes own 16-byte chunks; the
 // (row, weight) list is read 32 entries at a time (the next 32 prefetched) and broadcast with
@@ -469,6 +594,110 @@ dv_gather_bf16_kernel(const __nv_bfloat16* __restrict__ q, const DvEntry* __rest
     }
 }
 
+// The same gather over the GROUPED lists of dv_group_sort_kernel: the (row, weight) list of (image, patch) is
+// the concatenation, over the groups c, of entries[jl][c][segc[jl][c][p] .. segc[jl][c][p+1]).  The first
+// batch of the next group is requested before the current group's rows are consumed.
+template <typename OutT, int kU, int kW, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
+dv_gather_grouped_kernel(const __nv_bfloat16* __restrict__ q, const DvEntry* __restrict__ entries,
+                         const uint32_t* __restrict__ segc, const float* __restrict__ Tptr, int j0, int nj, int n_groups,
+                         int Nv, int D, int wps, int accumulate, OutT* __restrict__ dv) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 8 + warp;
+    const long long sid = wid / wps;
+    const int ch0 = (int)(wid - sid * wps) * 32 * kW + lane;
+    if (sid >= (long long)nj * Nv) return;
+    const int jl = (int)(sid / Nv), p = (int)(sid % Nv);
+    const char* qbase = reinterpret_cast<const char*>(q);
+    const uint32_t row_bytes = (uint32_t)D * 2u;
+    bool act[kW];
+    uint32_t lane_off[kW];
+#pragma unroll
+    for (int k = 0; k < kW; ++k) { act[k] = (ch0 + 32 * k) * 8 < D; lane_off[k] = act[k] ? (uint32_t)(ch0 + 32 * k) * 16u : 0u; }
+
+    float2 acc[kW][4];
+#pragma unroll
+    for (int k = 0; k < kW; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[k][c] = make_float2(0.f, 0.f);
+
+    const uint32_t* sg = segc + (size_t)jl * n_groups * (Nv + 1) + p;
+    const DvEntry* lists = entries + (size_t)jl * n_groups * kGroupRows;
+    // segment bounds of 32 groups at a time live in lane registers (lane c <-> group c0 + c): no dependent
+    // table load per group
+    uint32_t myE0 = 0, myE1 = 0;
+    if (lane < n_groups) { myE0 = sg[(size_t)lane * (Nv + 1)]; myE1 = sg[(size_t)lane * (Nv + 1) + 1]; }
+    uint32_t e0 = __shfl_sync(0xffffffffu, myE0, 0), e1 = __shfl_sync(0xffffffffu, myE1, 0);
+    DvEntry next; next.row = 0; next.w = 0.f;
+    if (e0 + lane < e1) next = lists[e0 + lane];
+    for (int c = 0; c < n_groups; ++c) {
+        const DvEntry* list = lists + (size_t)c * kGroupRows;
+        uint32_t f0 = 0, f1 = 0;                                   // the next group's segment
+        if (c + 1 < n_groups) {
+            if (((c + 1) & 31) == 0) {                             // refill the lane registers
+                myE0 = myE1 = 0;
+                if (c + 1 + lane < n_groups) { myE0 = sg[(size_t)(c + 1 + lane) * (Nv + 1)]; myE1 = sg[(size_t)(c + 1 + lane) * (Nv + 1) + 1]; }
+            }
+            f0 = __shfl_sync(0xffffffffu, myE0, (c + 1) & 31);
+            f1 = __shfl_sync(0xffffffffu, myE1, (c + 1) & 31);
+        }
+        const DvEntry* nlist = list + kGroupRows;
+        if (e0 >= e1) {                                            // empty here: `next` must become the next group's first batch
+            next.row = 0; next.w = 0.f;
+            if (f0 + lane < f1) next = nlist[f0 + lane];
+        }
+        for (uint32_t base = e0; base < e1; base += 32) {
+            const uint32_t my_row = next.row;
+            const float my_w = next.w;
+            next.row = 0; next.w = 0.f;
+            if (base + 32 < e1) { if (base + 32 + lane < e1) next = list[base + 32 + lane]; }
+            else if (f0 + lane < f1) next = nlist[f0 + lane];
+            const int n = min(32u, e1 - base);
+            for (int l = 0; l < n; l += kU) {
+                uint4 d[kU][kW];
+                float w[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int src = min(l + u, n - 1);
+                    const uint32_t row = __shfl_sync(0xffffffffu, my_row, src);
+                    const float ww = __shfl_sync(0xffffffffu, my_w, src);
+                    w[u] = (l + u < n) ? ww : 0.f;
+#pragma unroll
+                    for (int k = 0; k < kW; ++k)
+                        d[u][k] = __ldg(reinterpret_cast<const uint4*>(qbase + (row * row_bytes + lane_off[k])));
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+#pragma unroll
+                    for (int k = 0; k < kW; ++k) {
+                        ffma2_pair(acc[k][0], w[u], d[u][k].x); ffma2_pair(acc[k][1], w[u], d[u][k].y);
+                        ffma2_pair(acc[k][2], w[u], d[u][k].z); ffma2_pair(acc[k][3], w[u], d[u][k].w);
+                    }
+            }
+        }
+        e0 = f0; e1 = f1;
+    }
+    const float Tval = *Tptr;
+#pragma unroll
+    for (int k = 0; k < kW; ++k) {
+        if (!act[k]) continue;
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { o[2 * c] = acc[k][c].x * Tval; o[2 * c + 1] = acc[k][c].y * Tval; }
+        OutT* dst = dv + ((size_t)(j0 + jl) * Nv + p) * D + (ch0 + 32 * k) * 8;
+        if (accumulate) {
+            float prev[8];
+            LoadAs<OutT, 8>::get(dst, prev);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                o[2 * c] = __fmaf_rn(acc[k][c].x, Tval, prev[2 * c]);
+                o[2 * c + 1] = __fmaf_rn(acc[k][c].y, Tval, prev[2 * c + 1]);
+            }
+        }
+        StoreAs<OutT, 8>::put(dst, o);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // dT = sum g*clip / T : single CTA, fixed-order tree (deterministic)
 // ---------------------------------------------------------------------------------------
@@ -501,7 +730,7 @@ struct DvPlan {
     int qb;                 // queries per block
     int nblk;               // number of query blocks
     bool scratch;           // fp32 scratch needed (several blocks and a non-fp32 output)
-    size_t off_cnt, off_start, off_seg, off_entries, off_scratch, total;
+    size_t off_cnt, off_start, off_seg, off_segc, off_entries, off_scratch, total;
 };
 static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool out_f32, size_t block_bytes = kDvBlockBytes) {
     DvPlan pl;
@@ -512,7 +741,9 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool
     pl.nblk = (int)(((size_t)Bq + qb - 1) / qb);
     pl.scratch = pl.nblk > 1 && !out_f32;
     const size_t Mb = qb * Nq;                                       // rows per block
-    size_t jb = ((size_t)1 << 30) / (Mb * sizeof(DvEntry));
+    const size_t ng = (Mb + kGroupRows - 1) / kGroupRows;            // sort groups per block (grouped path)
+    const size_t Me = ng * kGroupRows;                               // entry slots per image (>= Mb)
+    size_t jb = ((size_t)1 << 30) / (Me * sizeof(DvEntry));
     if (pl.scratch) {                                                // keep the fp32 scratch <= 256 MB
         const size_t js = ((size_t)256 << 20) / ((size_t)Nv * D * 4);
         if (jb > js) jb = js;
@@ -524,7 +755,8 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool
     pl.off_cnt = o;     o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_start = o;   o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_seg = o;     o += align_up(jb * ((size_t)Nv + 1) * 4, 256);
-    pl.off_entries = o; o += align_up(jb * Mb * sizeof(DvEntry), 256);
+    pl.off_segc = o;    o += align_up(jb * ng * ((size_t)Nv + 1) * 4, 256);
+    pl.off_entries = o; o += align_up(jb * Me * sizeof(DvEntry), 256);
     pl.off_scratch = o; o += pl.scratch ? align_up(jb * (size_t)Nv * D * 4, 256) : 0;
     pl.total = o;
     return pl;
@@ -588,6 +820,39 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
                 const float* rs_b = row_scale + (size_t)q0 * Nq;
                 const float* g_b = g + (size_t)q0 * Bv;
                 const T* q_b = (const T*)q + (size_t)q0 * Nq * D;
+                if constexpr (sizeof(T) == 2) {
+                    if (Nv <= kGroupMaxNv && !(bwd_flags & TRIAD_BWD_GENERIC_DV)) {
+                        // grouped path: shared-memory sort per (image, row group) + gather over the grouped lists
+                        const int n_groups = ceil_div((int)Mb, kGroupRows);
+                        uint32_t* segc = (uint32_t*)((char*)ws + pl.off_segc);
+                        auto skern = dv_group_sort_kernel<IdxT>;
+                        static bool attr_set = false;
+                        if (!attr_set) {
+                            TRIAD_CUDA_CHECK(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                  (int)group_sort_smem(kGroupMaxNv)));
+                            attr_set = true;
+                        }
+                        skern<<<nj * n_groups, kGroupWarps * 32, group_sort_smem(Nv), st>>>(
+                            idx_b, g_b, rs_b, img_pitch, j0, n_groups, (int)Mb, Bv, Nq, Nv, nq_pad, segc, entries);
+                        TRIAD_LAUNCH_CHECK("dv_group_sort_kernel");
+                        const __nv_bfloat16* qb16 = (const __nv_bfloat16*)q_b;
+                        const bool wide_rows = D > 256;
+#define TRIAD_DVG_K(OUT, DST, J0, U, W, MB) do { \
+                            const int wps_ = ceil_div(D / 8, 32 * W); \
+                            const unsigned grid_ = (unsigned)(((long long)nj * Nv * wps_ + 7) / 8); \
+                            dv_gather_grouped_kernel<OUT, U, W, MB><<<grid_, 256, 0, st>>>(qb16, entries, segc, Tp, J0, nj, n_groups, Nv, D, wps_, b > 0, DST); \
+                        } while (0)
+#define TRIAD_DVG(OUT, DST, J0) \
+                        if (wide_rows) TRIAD_DVG_K(OUT, DST, J0, 4, 2, 3); else TRIAD_DVG_K(OUT, DST, J0, 8, 1, 3);
+                        if (pl.scratch) { TRIAD_DVG(float, scratch, 0) }
+                        else if (out_f32) { TRIAD_DVG(float, (float*)dv, j0) }
+                        else { TRIAD_DVG(__nv_bfloat16, (__nv_bfloat16*)dv, j0) }
+#undef TRIAD_DVG
+#undef TRIAD_DVG_K
+                        TRIAD_LAUNCH_CHECK("dv_gather_grouped_kernel");
+                        continue;
+                    }
+                }
                 dv_count_kernel<IdxT><<<sort_grid, kSortWarps * 32, smem, st>>>(idx_b, rs_b, img_pitch, j0, nj, nq, Nq, Nv, nq_pad, cnt);
                 TRIAD_LAUNCH_CHECK("dv_count_kernel");
                 dv_offsets_kernel<<<nj, 1024, 0, st>>>(cnt, nj, Nv, start, seg);
