@@ -54,6 +54,8 @@ extern "C" {
 #define TRIAD_FWD_FORCE_1CTA   2   /* tcgen05 kernel with cta_group::1 (debug / small shapes)        */
 #define TRIAD_FWD_DIVIDE_BY_T  4   /* S = <q,v> / T (retrieval.py:108) instead of <q,v> * T          */
 #define TRIAD_FWD_SYNC_CHUNKS  8   /* test aid: chunk-synchronous tile order (the V > 96 MB path) with 3-image chunks */
+#define TRIAD_FWD_PACK_ROWS   16   /* bf16 tensor-core path: rows whose row_scale is 0 (padded text tokens,
+                                      model.py:509-512) are dropped before the GEMM; their idx entries read 0 */
 
 int         triad_abi_version(void);
 const char* triad_status_string(int status);
@@ -78,6 +80,8 @@ int triad_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, void*
  * q [Bq,Nq,D], v [Bv,Nv,D] in `dtype`; clip fp32 [Bq,Bv]; idx as described above or NULL
  * (forward-only).  The Bq x Bv x Nq x Nv tensor is never written to memory. */
 size_t triad_maxmean_fwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
+/* the same, for a call that passes `flags` (TRIAD_FWD_PACK_ROWS needs room for the packed copy of q) */
+size_t triad_maxmean_fwd_workspace_bytes_ex(int Bq, int Bv, int Nq, int Nv, int D, int dtype, int flags);
 int triad_maxmean_fwd(const void* q, const void* v, const float* row_scale,
                       const float* temperature,
                       int Bq, int Bv, int Nq, int Nv, int D, int dtype,
@@ -127,6 +131,8 @@ int triad_infonce_finish(const float* clip_rows, int rows, int B, int row0,
 #define TRIAD_BWD_DQ_L1        8   /* tiled dq gathering through L1 instead of the TMA/shared-memory ring  */
 #define TRIAD_BWD_SMALL_BLOCKS 16   /* dv: 64 KB query blocks instead of 64 MB (test aid: multi-block path) */
 #define TRIAD_BWD_NO_PREFETCH  4   /* tiled dq without the prefetch.global.L1 look-ahead (A/B timing)      */
+#define TRIAD_BWD_PACK_ROWS   32   /* dq sweeps only the rows whose row_scale is non-zero (masked text tokens
+                                      get an exact zero gradient without being gathered for)                */
 size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
 int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
                       const float* clip, const float* row_scale, const float* temperature,

@@ -279,14 +279,19 @@ def test_backward_variants_agree(masked):
     for name, flags, f32 in (("default", 0, False), ("dq_l1", _lib.BWD_DQ_L1, False),
                              ("dq_l1_nopf", _lib.BWD_DQ_L1 | _lib.BWD_NO_PREFETCH, False),
                              ("dq_generic", _lib.BWD_GENERIC_DQ, False),
+                             ("dq_packed", _lib.BWD_PACK_ROWS, False),
+                             ("dv_generic", _lib.BWD_GENERIC_DV, False),
                              ("dv_blocks", _lib.BWD_SMALL_BLOCKS, False),
+                             ("dv_blocks_generic", _lib.BWD_SMALL_BLOCKS | _lib.BWD_GENERIC_DV, False),
                              ("dv_blocks_f32", _lib.BWD_SMALL_BLOCKS, True), ("dv_f32", 0, True)):
         dq, dv, dT = ops.maxmean_bwd(qd, vd, idx, g, clip, scale, Tt, dv_f32=f32, flags=flags)
         outs[name] = (dq, dv)
         assert rel_err(dq.cpu(), ref["dq"]) < 4e-3, name
         assert rel_err(dv.cpu(), ref["dv"]) < (1e-5 if f32 else 4e-3), name
-    for name in ("dq_l1", "dq_l1_nopf", "dq_generic"):          # same summation order: bit-identical
+    for name in ("dq_l1", "dq_l1_nopf", "dq_generic", "dq_packed"):          # same summation order: bit-identical
         assert torch.equal(outs[name][0], outs["default"][0]), name
+    assert torch.equal(outs["dv_generic"][1], outs["default"][1])             # grouped vs global sort: same lists
+    assert torch.equal(outs["dv_blocks_generic"][1], outs["dv_blocks"][1])
     assert torch.equal(outs["dv_f32"][1].to(torch.bfloat16), outs["default"][1])
     if masked:                                                   # padded tokens: exactly zero gradient
         assert outs["default"][0][mask.cuda() == 0].abs().max().item() == 0.0
@@ -317,11 +322,21 @@ def test_more_than_256_patches(flags, Nv):
     assert rel_err(qd.grad.cpu(), ref["dq"]) < 4e-3 and rel_err(vd.grad.cpu(), ref["dv"]) < 4e-3
 
 
-def test_masked_text_shape_cfg3_slice():
-    """cfg 3 flavour: 77 text tokens with ragged right-padded masks (n_i in [8,77])."""
+@pytest.mark.parametrize("pack", [True, False])
+@pytest.mark.parametrize("holes", [False, True])
+def test_masked_text_shape_cfg3_slice(pack, holes):
+    """cfg 3 flavour: 77 text tokens with ragged right-padded masks (n_i in [8,77]).  pack: zero-weight
+    rows are dropped before the GEMM (the default for bf16) vs. computed and multiplied by 0; both must give
+    the same clip / loss / gradients.  holes: masks that are not prefixes (zeros in the middle, an all-zero
+    caption) — the packing is by weight, not by length."""
     B, Nq, Nv, D = 48, 77, 256, 512
     q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=31, masked=True, min_len=8)
+    if holes:
+        mask[3, 2:5] = 0
+        mask[7, 0] = 0
+        mask[11] = 0                    # clamp(sum,1e-7) branch of model.py:511: clip row of zeros
     m = _model(1.5)
+    m.triad_pack_masked_rows = pack
     qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
     clip, tok = m.compute_all_similarities_tv(qd, vd, mask.cuda())
     loss, stats = m.compute_contrastive_loss_tv(clip, tok)
@@ -334,6 +349,12 @@ def test_masked_text_shape_cfg3_slice():
     assert rel_err(qd.grad.cpu(), ref["dq"]) < 4e-3 and rel_err(vd.grad.cpu(), ref["dv"]) < 4e-3
     # padded tokens receive exactly zero gradient (mask multiplies their maxima by 0, model.py:510)
     assert qd.grad[mask.cuda() == 0].abs().max().item() == 0.0
+    assert tok.packed == pack
+    if pack:       # the winners recorded by the packed forward are the full forward's, on every kept row
+        from triad_b200 import ops
+        kept = mask.bool()[:, None, :].expand(B, B, Nq)
+        got = ops.idx_to_reference_layout(tok.idx_t, B, Nq).cpu()
+        assert torch.equal(got[kept], tok.argmax().cpu()[kept])
 
 
 def test_retrieval_against_reference_goldens():

@@ -53,7 +53,14 @@ def main():
     g, sums = ops.infonce_finish(clip, B, 0, row_lse, col_part.reshape(1, 2, B))
     print(f"shape Bq={Bq} Bv={Bv} Nq={Nq} Nv={Nv} D={D} masked={mask is not None}  block loss sum={sums[0].item() / (2 * B):.6f}")
 
-    t_fwd = timeit(lambda: ops.maxmean_fwd(q, v, scale, T), iters)
+    pack_f = _lib.FWD_PACK_ROWS if mask is not None else 0        # what the drop-in does for masked bf16 queries
+    pack_b = _lib.BWD_PACK_ROWS if mask is not None else 0
+    if mask is not None:
+        t_unp = timeit(lambda: ops.maxmean_fwd(q, v, scale, T), iters)
+        print(f"fwd without row packing {t_unp:.3f} ms")
+        clip_p, idx_p = ops.maxmean_fwd(q, v, scale, T, flags=pack_f)
+        print("packed vs unpacked clip exact:", torch.equal(clip_p, clip))
+    t_fwd = timeit(lambda: ops.maxmean_fwd(q, v, scale, T, flags=pack_f), iters)
     t_nce = timeit(lambda: ops.infonce_finish(clip, B, 0, *ops.infonce_partial(clip, B, 0)[:1],
                                                col_part.reshape(1, 2, B)), iters)
     tf = 2.0 * Bv * (mask.sum().item() if mask is not None else Bq * Nq) * Nv * D / 1e12
@@ -63,7 +70,7 @@ def main():
         return ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=dq, need_dv=dv, need_dT=False, flags=flags)
 
     outs = {}
-    for name, dq_, dv_, fl in (("dq tiled", True, False, 0), ("dq tiled L1", True, False, _lib.BWD_DQ_L1),
+    for name, dq_, dv_, fl in (("dq tiled", True, False, pack_b), ("dq unpacked", True, False, 0), ("dq tiled L1", True, False, _lib.BWD_DQ_L1),
                                ("dq tiled L1 nopf", True, False, _lib.BWD_DQ_L1 | _lib.BWD_NO_PREFETCH),
                                ("dq generic", True, False, _lib.BWD_GENERIC_DQ),
                                ("dv default", False, True, 0), ("dv generic", False, True, _lib.BWD_GENERIC_DV)):
@@ -76,7 +83,7 @@ def main():
           " exact:", torch.equal(outs["dq tiled"], outs["dq generic"]))
     print("dv default vs generic rel diff", rel(outs["dv default"], outs["dv generic"]),
           " exact:", torch.equal(outs["dv default"], outs["dv generic"]))
-    t_all = timeit(lambda: ops.maxmean_bwd(q, v, idx, g, clip, scale, T), iters)
+    t_all = timeit(lambda: ops.maxmean_bwd(q, v, idx, g, clip, scale, T, flags=pack_b), iters)
     tot = t_fwd + t_nce + t_all
     print(f"bwd (dq+dv+dT) {t_all:.3f} ms    fwd+nce+bwd {tot:.3f} ms  = {Bq * Bv / tot / 1e3:.2f} M pairs/s per GPU")
 

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libtriad_b200.so")
 
 OK = 0
 DTYPE_F32, DTYPE_BF16 = 0, 1
-FWD_DEFAULT, FWD_FORCE_SIMT, FWD_FORCE_1CTA, FWD_DIVIDE_BY_T, FWD_SYNC_CHUNKS = 0, 1, 2, 4, 8
-BWD_DEFAULT, BWD_GENERIC_DQ, BWD_GENERIC_DV, BWD_NO_PREFETCH, BWD_DQ_L1, BWD_SMALL_BLOCKS = 0, 1, 2, 4, 8, 16
+FWD_DEFAULT, FWD_FORCE_SIMT, FWD_FORCE_1CTA, FWD_DIVIDE_BY_T, FWD_SYNC_CHUNKS, FWD_PACK_ROWS = 0, 1, 2, 4, 8, 16
+BWD_DEFAULT, BWD_GENERIC_DQ, BWD_GENERIC_DV, BWD_NO_PREFETCH, BWD_DQ_L1, BWD_SMALL_BLOCKS, BWD_PACK_ROWS = 0, 1, 2, 4, 8, 16, 32
 
 # name -> (restype, argtypes); must list every symbol of include/triad_b200.h
 SIGNATURES = {
@@ -26,6 +26,7 @@ SIGNATURES = {
     "triad_device_check": (c_int, [c_int]),
     "triad_row_scale": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "triad_maxmean_fwd_workspace_bytes": (c_size_t, [c_int] * 6),
+    "triad_maxmean_fwd_workspace_bytes_ex": (c_size_t, [c_int] * 7),
     "triad_maxmean_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),

@@ -226,7 +226,11 @@ constexpr uint32_t kSmemBytes = kVS * kVStageBytes + kWBytes + kIdxBytes + 2 * 8
 __global__ void __launch_bounds__(kThreads, 1)
 dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __restrict__ idx, const float* __restrict__ g,
                const float* __restrict__ row_scale, const float* __restrict__ Tptr,
-               int M, int Bv, int Nq, int Nv, int D, int nq_pad, int g_vec, __nv_bfloat16* __restrict__ dq, int* abort_flag) {
+               int M, int Bv, int Nq, int Nv, int D, int nq_pad, int g_vec, __nv_bfloat16* __restrict__ dq, int* abort_flag,
+               const int* __restrict__ pack_off, const int* __restrict__ rowmap) {
+    // packed rows (pack.cu): the tile rows are the KEPT rows; rows with zero weight were zeroed by the launcher
+    const int M_eff = pack_off ? pack_off[M / Nq] : M;
+    if ((int)blockIdx.y * kRows >= M_eff) return;
     extern __shared__ unsigned char dq3_smem[];
     const uint32_t s0 = smem_u32(dq3_smem);
     const uint32_t sbase = (s0 + 127u) & ~127u;
@@ -244,8 +248,8 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     // ---- staging role: thread t = tile row t.  A warp stages exactly the 32 rows it later gathers
     //      for, so the staging buffers are warp-private: __syncwarp is all the ordering they need and
     //      the warps of a CTA only meet at the V ring's mbarriers (they may drift up to kVS-1 images).
-    const int rs = row0 + t;
-    const bool rs_valid = rs < M;
+    const bool rs_valid = row0 + t < M_eff;
+    const int rs = rs_valid ? (rowmap ? rowmap[row0 + t] : row0 + t) : 0;      // original row
     const int qi = rs_valid ? rs / Nq : 0;
     const size_t pitch = (size_t)(M / Nq) * nq_pad;
     const uint8_t* idx_row = idx + (size_t)qi * nq_pad + (rs_valid ? rs - qi * Nq : 0);
@@ -354,8 +358,9 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     const float Tval = *Tptr;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int r = row0 + rb + k;
-        if (r < M) {
+        const int rk = row0 + rb + k;
+        if (rk < M_eff) {
+            const int r = rowmap ? rowmap[rk] : rk;
             const float s = Tval * row_scale[r];
             uint4 o;
             uint32_t* w32 = reinterpret_cast<uint32_t*>(&o);
@@ -375,7 +380,7 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
 bool dq_smem_supported(int Nv, int D, int dtype) { return dtype == TRIAD_DTYPE_BF16 && D % dq3::kSlice == 0 && Nv <= dq3::kMaxNv; }
 
 int launch_dq_smem(const void* v, const void* idx, const float* g, const float* row_scale, const float* Tp,
-                   int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, cudaStream_t st) {
+                   int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, const int* pack_maps, cudaStream_t st) {
     using namespace dq3;
     static bool attr_set = false;
     if (!attr_set) {
@@ -390,8 +395,10 @@ int launch_dq_smem(const void* v, const void* idx, const float* g, const float* 
     if (rc) return rc;
     const dim3 grid((unsigned)(D / kSlice), (unsigned)ceil_div(M, kRows));
     const int g_vec = (Bv % 4 == 0) && (((uintptr_t)g & 15) == 0);
+    if (pack_maps) TRIAD_CUDA_CHECK(cudaMemsetAsync(dq, 0, (size_t)M * D * 2, st));      // rows that were dropped: zero gradient
     dq_smem_kernel<<<grid, kThreads, kSmemBytes, st>>>(mv, (const uint8_t*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D,
-                                                      nq_padded(Nq), g_vec, (__nv_bfloat16*)dq, abort_flag);
+                                                      nq_padded(Nq), g_vec, (__nv_bfloat16*)dq, abort_flag,
+                                                      pack_maps, pack_maps ? pack_maps + M / Nq + 1 : nullptr);
     TRIAD_LAUNCH_CHECK("dq_smem_kernel");
     return TRIAD_OK;
 }

@@ -65,10 +65,25 @@ extern "C" int triad_row_scale(const int64_t* mask, int Bq, int Nq, float* row_s
     return launch_row_scale(mask, Bq, Nq, row_scale, (cudaStream_t)stream);
 }
 
-extern "C" size_t triad_maxmean_fwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype) {
-    (void)Nv; (void)D; (void)dtype;
+// packed forward (TRIAD_FWD_PACK_ROWS): [0,256) control | partial sums (packed layout) | packing maps | packed q
+static size_t fwd_part_bytes_packed(int Bq, int Bv, int Nq) {
+    return align_up((size_t)Bv * Bq * packed_pieces(Nq) * sizeof(float), 256);
+}
+
+extern "C" size_t triad_maxmean_fwd_workspace_bytes_ex(int Bq, int Bv, int Nq, int Nv, int D, int dtype, int flags) {
+    (void)Nv;
     if (Bq <= 0 || Bv <= 0 || Nq <= 0) return 0;
-    return 256 + fwd_part_bytes(Bq * Nq, Bv, Nq);
+    size_t n = 256 + fwd_part_bytes(Bq * Nq, Bv, Nq);
+    if ((flags & TRIAD_FWD_PACK_ROWS) && dtype == TRIAD_DTYPE_BF16 && D > 0) {
+        const size_t packed = 256 + fwd_part_bytes_packed(Bq, Bv, Nq) + pack_map_bytes(Bq, Nq) +
+                              align_up((size_t)Bq * Nq * D * 2, 256);
+        if (packed > n) n = packed;
+    }
+    return n;
+}
+
+extern "C" size_t triad_maxmean_fwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype) {
+    return triad_maxmean_fwd_workspace_bytes_ex(Bq, Bv, Nq, Nv, D, dtype, 0);
 }
 
 static int fwd_impl(const void* q, const void* v, const float* row_scale, const float* temperature, int inv_T,
@@ -80,7 +95,7 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
         return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_fwd: bad shape (need D % 8 == 0, Nv <= 65535)");
     if ((long long)Bq * Nq > 0x7fffffffLL) return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_fwd: Bq*Nq overflows int32");
     if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)ws) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_fwd: q, v and ws must be 16-byte aligned");
-    if (ws_bytes < triad_maxmean_fwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype)) return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_fwd: workspace too small");
+    if (ws_bytes < triad_maxmean_fwd_workspace_bytes_ex(Bq, Bv, Nq, Nv, D, dtype, flags)) return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_fwd: workspace too small");
 
     const int M = Bq * Nq;
     int* abort_flag = (int*)ws;
@@ -89,12 +104,27 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
 
     const bool use_tc = dtype == TRIAD_DTYPE_BF16 && !(flags & TRIAD_FWD_FORCE_SIMT) && tc_supported(Nv, D);
     int rc;
+    if (use_tc && (flags & TRIAD_FWD_PACK_ROWS)) {
+        // masked text queries: drop the zero-weight rows before the tensor cores (pack.cu)
+        char* maps = (char*)ws + 256 + fwd_part_bytes_packed(Bq, Bv, Nq);
+        void* qp = maps + pack_map_bytes(Bq, Nq);
+        rc = launch_pack_map(row_scale, Bq, Nq, maps, st);
+        if (rc) return rc;
+        rc = launch_pack_copy(q, maps, Bq, Nq, D, 2, qp, st);
+        if (rc) return rc;
+        if (idx) TRIAD_CUDA_CHECK(cudaMemsetAsync(idx, 0, (size_t)Bv * Bq * nq_padded(Nq) * (Nv > 256 ? 2 : 1), st));
+        const int cta_group = (flags & TRIAD_FWD_FORCE_1CTA) ? 1 : 2;
+        rc = launch_maxmean_tc(qp, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags,
+                               (const int*)maps, st);
+        if (rc) return rc;
+        return launch_finalize_clip_packed(part, (const int*)maps, Bq, Bv, Nq, clip, st);
+    }
     if (use_tc) {
         // A single row tile of <= 128 tokens (one text query against a gallery): cta_group::1 — a pair would
         // spend a 256-row MMA on <= 128 rows, and at one tile per image that MMA time equals the HBM time of
         // the image, leaving no slack to overlap; alone, each SM streams its own images at twice that rate.
         const int cta_group = ((flags & TRIAD_FWD_FORCE_1CTA) || M <= 128) ? 1 : 2;
-        rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags, st);
+        rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags, nullptr, st);
     } else {
         rc = launch_maxmean_simt(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, dtype, part, idx, st);
     }

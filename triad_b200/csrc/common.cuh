@@ -58,13 +58,22 @@ int launch_maxmean_simt(const void* q, const void* v, const float* row_scale, co
                         float* part, void* idx, cudaStream_t st);   // idx: [Bv][M/Nq][nq_padded(Nq)]
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
-                      float* part, void* idx, int* abort_flag, int cta_group, int flags, cudaStream_t st);
+                      float* part, void* idx, int* abort_flag, int cta_group, int flags, const int* pack_maps,
+                      cudaStream_t st);
 int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
+// packed rows (pack.cu): maps = off[Bq+1] | rowmap[Bq*Nq] | scratch
+size_t pack_map_bytes(int Bq, int Nq);
+int launch_pack_map(const float* row_scale, int Bq, int Nq, void* maps, cudaStream_t st);
+int launch_pack_copy(const void* q, const void* maps, int Bq, int Nq, int D, int elt_bytes, void* qp, cudaStream_t st);
+int launch_finalize_clip_packed(const float* part, const int* pack_off, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
+// partial sums of the packed forward: part[(j*Bq + i)*pieces + piece], piece = (32-row group of the packed row)
+// - (group of the query's first packed row); a query of <= Nq kept rows spans at most (Nq+30)/32 + 1 groups
+static inline int packed_pieces(int Nq) { return (Nq + 30) / 32 + 1; }
 bool tc_supported(int Nv, int D);
 // tiled dQ of the backward, bf16 only — bwd_dq_tile.cu (TMA/shared-memory gather, and the L1-resident variant)
 bool dq_smem_supported(int Nv, int D, int dtype);
 int launch_dq_smem(const void* v, const void* idx, const float* g, const float* row_scale, const float* Tp,
-                   int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, cudaStream_t st);
+                   int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, const int* pack_maps, cudaStream_t st);
 bool dq_tile_supported(int D, int dtype);
 int launch_dq_tile(const void* v, const void* idx, int idx_bytes, const float* g, const float* row_scale,
                    const float* Tp, int M, int Bv, int Nq, int Nv, int D, int prefetch, void* dq, cudaStream_t st);
@@ -109,6 +118,21 @@ __device__ __forceinline__ void store_group_partials(float* __restrict__ part, i
         const int qfirst = (g * 32) / Nq;
         part[((size_t)j * G + g) * S + (qid - qfirst)] = val;
     }
+}
+
+// Packed rows: the same segmented reduction; the head lane of each query segment stores the segment's sum in
+// the query's slot for this 32-row group.
+__device__ __forceinline__ void store_group_partials_packed(float* __restrict__ part, int j, int Bq, int pieces,
+                                                            int qid, int piece, float val, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(0xffffffffu, val, o);
+        int tq = __shfl_down_sync(0xffffffffu, qid, o);
+        if (lane + o < 32 && tq == qid) val += t;
+    }
+    const int prev = __shfl_up_sync(0xffffffffu, qid, 1);
+    const bool head = (lane == 0) || (prev != qid);
+    if (head && qid != 0x7fffffff) part[((size_t)j * Bq + qid) * pieces + piece] = val;
 }
 
 #endif  // __CUDACC__

@@ -766,7 +766,7 @@ template <typename T, typename IdxT>
 static int bwd_typed(const void* q, const void* v, const void* idx, const float* g,
                      const float* clip, const float* row_scale, const float* Tp,
                      int Bq, int Bv, int Nq, int Nv, int D,
-                     void* dq, void* dv, int dv_f32, float* dT, void* ws, int bwd_flags, cudaStream_t st) {
+                     void* dq, void* dv, int dv_f32, float* dT, void* ws, size_t pack_maps_offset, int bwd_flags, cudaStream_t st) {
     const int M = Bq * Nq;
     const int nq_pad = nq_padded(Nq);
     constexpr int E = Vec16<T>::kElems;
@@ -774,7 +774,15 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
     if (dq && (kch < 1 || kch > 4)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
     if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_smem_supported(Nv, D, TRIAD_DTYPE_BF16) &&
         !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1))) {
-        const int rc = launch_dq_smem(v, idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, dq, (int*)ws, st);
+        // TRIAD_BWD_PACK_ROWS (masked text queries): only the rows with a non-zero weight are swept
+        const int* pack_maps = nullptr;
+        if (bwd_flags & TRIAD_BWD_PACK_ROWS) {
+            void* maps = (char*)ws + pack_maps_offset;
+            const int rcm = launch_pack_map(row_scale, Bq, Nq, maps, st);
+            if (rcm) return rcm;
+            pack_maps = (const int*)maps;
+        }
+        const int rc = launch_dq_smem(v, idx, g, row_scale, Tp, M, Bv, Nq, Nv, D, dq, (int*)ws, pack_maps, st);
         if (rc) return rc;
     } else if (dq && sizeof(T) == 2 && dq_tile_supported(D, TRIAD_DTYPE_BF16) && !(bwd_flags & TRIAD_BWD_GENERIC_DQ)) {
         const int rc = launch_dq_tile(v, idx, (int)sizeof(IdxT), g, row_scale, Tp, M, Bv, Nq, Nv, D,
@@ -919,7 +927,7 @@ extern "C" size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int 
             const size_t t = dv_plan(Bq, Bv, Nq, Nv, D, eb, f32 != 0, small ? ((size_t)64 << 10) : kDvBlockBytes).total;
             if (t > best) best = t;
         }
-    return best;
+    return best + pack_map_bytes(Bq, Nq);                 // the packing maps of TRIAD_BWD_PACK_ROWS live at the end
 }
 
 extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
@@ -933,15 +941,16 @@ extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, 
         return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_bwd: bad shape");
     if (dtype != TRIAD_DTYPE_F32 && dtype != TRIAD_DTYPE_BF16) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: dtype");
     if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)dq | (uintptr_t)dv | (uintptr_t)ws) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_bwd: 16-byte alignment");
-    if (!ws || ws_bytes < (dv ? triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) : (size_t)256))
+    if (!ws || ws_bytes < ((dv || (flags & TRIAD_BWD_PACK_ROWS)) ? triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) : (size_t)256))
         return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     TRIAD_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, st));
     const bool wide = Nv > 256;
+    const size_t pmo = triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) - pack_map_bytes(Bq, Nq);
     if (dtype == TRIAD_DTYPE_BF16) {
-        return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st)
-                    : bwd_typed<__nv_bfloat16, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st);
+        return wide ? bwd_typed<__nv_bfloat16, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, pmo, flags, st)
+                    : bwd_typed<__nv_bfloat16, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, pmo, flags, st);
     }
-    return wide ? bwd_typed<float, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st)
-                : bwd_typed<float, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, flags, st);
+    return wide ? bwd_typed<float, uint16_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, pmo, flags, st)
+                : bwd_typed<float, uint8_t>(q, v, idx, g, clip, row_scale, temperature, Bq, Bv, Nq, Nv, D, dq, dv, dv_f32, dT, ws, pmo, flags, st);
 }

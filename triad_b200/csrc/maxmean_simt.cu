@@ -67,6 +67,30 @@ int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip,
     return TRIAD_OK;
 }
 
+// packed rows: clip[i][j] = sum of the query's pieces (one per 32-row group its kept rows touch), ascending
+__global__ void finalize_clip_packed_kernel(const float* __restrict__ part, const int* __restrict__ off, int Bq, int Bv,
+                                            int pieces, float* __restrict__ clip) {
+    const int nib = (Bq + blockDim.x - 1) / blockDim.x;
+    const int i = (blockIdx.x % nib) * blockDim.x + threadIdx.x;
+    const int j = blockIdx.x / nib;
+    if (i >= Bq) return;
+    const int k0 = off[i], k1 = off[i + 1];
+    float acc = 0.f;
+    if (k1 > k0) {
+        const int np = ((k1 - 1) >> 5) - (k0 >> 5) + 1;
+        const float* pp = part + ((size_t)j * Bq + i) * pieces;
+        for (int s = 0; s < np; ++s) acc += pp[s];
+    }
+    clip[(size_t)i * Bv + j] = acc;
+}
+
+int launch_finalize_clip_packed(const float* part, const int* pack_off, int Bq, int Bv, int Nq, float* clip, cudaStream_t st) {
+    dim3 grid((unsigned)(ceil_div(Bq, 128) * Bv));
+    finalize_clip_packed_kernel<<<grid, 128, 0, st>>>(part, pack_off, Bq, Bv, packed_pieces(Nq), clip);
+    TRIAD_LAUNCH_CHECK("finalize_clip_packed_kernel");
+    return TRIAD_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // SIMT forward: one CTA = one 32-row group x one image; 256 threads as 16 (rows/2) x 16 (cols/4)
 // ---------------------------------------------------------------------------------------

@@ -69,6 +69,11 @@ struct Params {
     float* part;
     uint8_t* idx;
     int* abort_flag;
+    // packed rows (pack.cu): the GEMM rows are the kept rows only; maps = off[Bq+1] | rowmap[M], M' = off[Bq]
+    const int* pack_off;     // NULL = rows are the original rows
+    const int* rowmap;
+    int Bq;
+    int pieces;              // packed partial layout: part[(j*Bq + i)*pieces + (group - first group of query i)]
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -199,8 +204,11 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t n_clusters = gridDim.x / kCtaGroup;
 
     // work items are (m-tile, image) pairs; each is n_sub consecutive accumulator tiles
+    // packed rows: the number of kept rows is only known on the device (no host synchronisation)
+    const int M_eff = p.pack_off ? p.pack_off[p.Bq] : p.M;
+    const int n_m_eff = p.pack_off ? (M_eff + kBlockM * kCtaGroup - 1) / (kBlockM * kCtaGroup) : p.n_m;
     TileIter it;
-    it.init(p.n_m, p.Bv, p.C, p.sync, cluster_id, n_clusters);
+    it.init(n_m_eff, p.Bv, p.C, p.sync, cluster_id, n_clusters);
     const int n_sub = kSub ? p.n_sub : 1;
 
     const int n_half = p.n_umma / kCtaGroup;                    // patch rows this CTA loads per image
@@ -306,17 +314,20 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (p.inv_T) Tval = 1.0f / Tval;
         int prev_m = -1; float rs = 0.f; uint32_t t_cnt = 0;
         size_t idx_off = 0;                       // (i*nq_pad + a) of this thread's row
+        int r_orig = -1, qi = 0, piece = 0;       // original row (-1: no such row), its query, packed partial slot
         const size_t idx_pitch = (size_t)(p.M / p.Nq) * p.nq_pad;
         float R_run = 0.f; int best_run = 0;      // running (rounded max, first argmax) across the sub-tiles of an image
         bool alive = true;
         Tile t;
         while (alive && it.next(t)) {
             const int row0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;
-            const int r = row0 + lane;
+            const int r = row0 + lane;                   // GEMM row (packed row number when rows are packed)
             if (t.m != prev_m) {
-                rs = (r < p.M) ? p.row_scale[r] : 0.f;
-                const int qi = r / p.Nq;
-                idx_off = (size_t)qi * p.nq_pad + (r - qi * p.Nq);
+                r_orig = (r < M_eff) ? (p.pack_off ? p.rowmap[r] : r) : -1;
+                rs = (r_orig >= 0) ? p.row_scale[r_orig] : 0.f;
+                qi = (r_orig >= 0) ? r_orig / p.Nq : 0x7fffffff;
+                idx_off = (r_orig >= 0) ? (size_t)qi * p.nq_pad + (r_orig - qi * p.Nq) : 0;
+                if (p.pack_off && r_orig >= 0) piece = (row0 >> 5) - (p.pack_off[qi] >> 5);
                 prev_m = t.m;
             }
           for (int sb = 0; sb < n_sub; ++sb, ++t_cnt) {
@@ -382,12 +393,13 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (sb == 0 || R > R_run) { R_run = R; best_run = best + sb * kMaxN; }
           }
             if (!alive) break;
-            if (p.idx != nullptr && r < p.M) {
+            if (p.idx != nullptr && r_orig >= 0) {
                 if (p.idx16) reinterpret_cast<uint16_t*>(p.idx)[(size_t)t.j * idx_pitch + idx_off] = (uint16_t)best_run;
                 else p.idx[(size_t)t.j * idx_pitch + idx_off] = (uint8_t)best_run;
             }
-            const float val = (r < p.M) ? R_run * rs : 0.f;
-            store_group_partials(p.part, t.j, row0 >> 5, p.G, p.S, row0, p.M, p.Nq, val, lane);
+            const float val = (r_orig >= 0) ? R_run * rs : 0.f;
+            if (p.pack_off == nullptr) store_group_partials(p.part, t.j, row0 >> 5, p.G, p.S, row0, p.M, p.Nq, val, lane);
+            else store_group_partials_packed(p.part, t.j, p.Bq, p.pieces, qi, piece, val, lane);
         }
     }
 
@@ -473,7 +485,8 @@ bool tc_supported(int Nv, int D) { return Nv >= 1 && Nv <= 65535 && D % tc::kBlo
 
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
-                      float* part, void* idx, int* abort_flag, int cta_group, int flags, cudaStream_t st) {
+                      float* part, void* idx, int* abort_flag, int cta_group, int flags, const int* pack_maps,
+                      cudaStream_t st) {
     using namespace tc;
     if (!tc_supported(Nv, D)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: needs D in {64,...,512} (multiple of 64)");
     const int tile_rows = kBlockM * cta_group;
@@ -519,6 +532,10 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     p.nq_pad = nq_padded(Nq);
     p.inv_T = inv_T;
     p.row_scale = row_scale; p.T = T; p.part = part; p.idx = (uint8_t*)idx; p.abort_flag = abort_flag;
+    p.Bq = M / Nq;
+    p.pack_off = pack_maps;                                   // q then points at the PACKED rows
+    p.rowmap = pack_maps ? pack_maps + p.Bq + 1 : nullptr;
+    p.pieces = packed_pieces(Nq);
 
     CUtensorMap mq, mv;
     {

@@ -26,6 +26,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import ops
+from . import _lib as _lib_flags
 
 
 class TokenSims:
@@ -37,13 +38,24 @@ class TokenSims:
         self.clip = clip_f32            # fp32 (Bq,Bv), attached to the autograd graph
         self.idx_t = idx                # [Bv, Bq*nq_pad] uint8/uint16 (library layout)
         self.prefix = prefix
+        self.packed = False
+        self.fwd_flags = 0
         self.shape = torch.Size((q.shape[0], v.shape[0], q.shape[1], v.shape[1]))
         self.dtype = q.dtype
         self.device = q.device
 
     def argmax(self) -> torch.Tensor:
-        """(Bq,Bv,Nq) int64 in the reference's layout: torch.max(token_sims, dim=3)[1]."""
-        return ops.idx_to_reference_layout(self.idx_t, self.shape[0], self.shape[2])
+        """(Bq,Bv,Nq) int64 in the reference's layout: torch.max(token_sims, dim=3)[1].
+
+        When padded tokens were dropped from the training forward (``packed``), their winners — which
+        the reference computes although nothing depends on them — are produced here by one forward over
+        all rows (inspection / parity tests only; not on the training path)."""
+        idx = self.idx_t
+        if self.packed:
+            T = ops.temperature_tensor(self.temperature, self.device)
+            _, idx = ops.maxmean_fwd(self.q.detach(), self.v.detach(), self.row_scale, T, want_idx=True,
+                                     flags=self.fwd_flags & ~_lib_flags.FWD_PACK_ROWS)
+        return ops.idx_to_reference_layout(idx, self.shape[0], self.shape[2])
 
     def materialize(self) -> torch.Tensor:
         """Dense token_sims exactly as the reference builds it (model.py:384-387).  Debug /
@@ -134,6 +146,9 @@ class TriadSimilarityMixin:
 
     #: forwarded to triad_maxmean_fwd (tests use it to pin a kernel variant)
     triad_fwd_flags: int = 0
+    #: drop zero-weight (padded) text tokens before the GEMM (bf16 tensor-core path); their argmax entries are
+    #: then only produced on demand by TokenSims.argmax()
+    triad_pack_masked_rows: bool = True
     #: evaluate the reference's regularisation terms (model.py:394-428, :516-542) in the loss methods
     triad_regularizers: bool = True
 
@@ -147,9 +162,14 @@ class TriadSimilarityMixin:
                             f"{q_feats.dtype} / {visual_feats.dtype}")
         Bq, Nq, _ = q_feats.shape
         scale = ops.row_scale(attention_mask, Bq, Nq, q_feats.device)
-        clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale,
-                                                int(self.triad_fwd_flags))
+        flags = int(self.triad_fwd_flags)
+        # padded text tokens (weight 0, model.py:509-512) are dropped before the tensor cores
+        if attention_mask is not None and q_feats.dtype == torch.bfloat16 and self.triad_pack_masked_rows:
+            flags |= _lib_flags.FWD_PACK_ROWS
+        clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale, flags)
         handle = TokenSims(q_feats, visual_feats, self.temperature, scale, attention_mask, clip, idx, prefix)
+        handle.packed = bool(flags & _lib_flags.FWD_PACK_ROWS)
+        handle.fwd_flags = flags
         # The reference's clip_sims dtype: bf16 for AV under autocast (mean of bf16 maxima,
         # model.py:391), fp32 for TV (mask.float() promotes, model.py:509-512) and for fp32 inputs.
         out = clip.to(q_feats.dtype) if attention_mask is None else clip

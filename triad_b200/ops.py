@@ -106,7 +106,7 @@ def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.
     dt = _dtype_code(q)
     clip = torch.empty(Bq, Bv, dtype=torch.float32, device=q.device)
     idx = torch.empty(Bv, Bq * nq_padded(Nq), dtype=idx_dtype(Nv), device=q.device) if want_idx else None
-    nws = lib.triad_maxmean_fwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dt)
+    nws = lib.triad_maxmean_fwd_workspace_bytes_ex(Bq, Bv, Nq, Nv, D, dt, int(flags))
     ws = _Workspace.get(nws, q.device, "fwd")
     check(lib.triad_maxmean_fwd(q.data_ptr(), v.data_ptr(), scale.data_ptr(), T.data_ptr(),
                                 Bq, Bv, Nq, Nv, D, dt, clip.data_ptr(), _ptr(idx),
@@ -177,6 +177,8 @@ class MaxMeanSimilarity(torch.autograd.Function):
         T = temperature_tensor(temperature, q.device)
         clip, idx = maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
         ctx.save_for_backward(q, v, T, scale, idx, clip)
+        # rows dropped in the forward (zero weight) have no winners recorded: the backward must skip them too
+        ctx.bwd_flags = _lib.BWD_PACK_ROWS if (flags & _lib.FWD_PACK_ROWS) else 0
         ctx.mark_non_differentiable(idx)
         ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
         ctx.t_dtype = temperature.dtype if isinstance(temperature, torch.Tensor) else None
@@ -186,7 +188,7 @@ class MaxMeanSimilarity(torch.autograd.Function):
     def backward(ctx, g, _gidx):
         q, v, T, scale, idx, clip = ctx.saved_tensors
         need_dq, need_dv, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        dq, dv, dT = maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq, need_dv, need_dT)
+        dq, dv, dT = maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq, need_dv, need_dT, flags=ctx.bwd_flags)
         if dT is not None and ctx.t_shape is not None:
             dT = dT.reshape(ctx.t_shape).to(ctx.t_dtype)
         return dq, dv, dT, None, None
