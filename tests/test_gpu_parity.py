@@ -357,6 +357,21 @@ def test_masked_text_shape_cfg3_slice(pack, holes):
         assert torch.equal(got[kept], tok.argmax().cpu()[kept])
 
 
+@pytest.mark.parametrize("masked", [False, True])
+def test_sharded_step_single_rank_cuda(masked):
+    """triad_b200.dist.sharded_contrastive_step with the product (CUDA) kernels on one rank — the code every
+    rank runs under torchrun (collectives are identity at world size 1; the gloo tests cover them)."""
+    from triad_b200.dist import sharded_contrastive_step
+    B, Nq, Nv, D = 12, 40, 96, 128
+    q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=51, masked=masked, min_len=2)
+    ref = O.contrastive_step_closed_form(q, v, 1.5, mask)
+    out = sharded_contrastive_step(q.cuda(), v.cuda(), torch.tensor(1.5, device="cuda"),
+                                   mask.cuda() if masked else None)
+    assert abs(out["loss"].item() - ref["loss"].item()) < 1e-5 * ref["loss"].item()
+    assert rel_err(out["dq"].cpu(), ref["dq"]) < 4e-3 and rel_err(out["dv"].cpu(), ref["dv"]) < 4e-3
+    assert abs(out["dT"].item() - ref["dT"].item()) < 1e-4 * (ref["g"].abs() * ref["clip"].abs().double()).sum().item()
+
+
 def test_retrieval_against_reference_goldens():
     from triad_b200 import retrieval as R
     gold = load_golden("retrieval")

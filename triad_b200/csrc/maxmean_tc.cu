@@ -505,25 +505,27 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     p.idx16 = Nv > 256;
     p.num_kb = D / kBlockK;
     p.n_m = n_m;
-    // Tile order (TileIter).  V small: any order, V stays in L2 (up to ~96 MB — cfg 2 is 67 MB — the clusters
-    // may be anywhere in V).  V larger than L2: if there are enough query tiles to give every cluster a few
-    // items per ~32 MB image chunk, all clusters walk the same chunk at the same time (V is read from HBM once);
-    // otherwise (retrieval: one or a few query tiles against a huge gallery) each cluster keeps to its own
-    // images and runs all query tiles against a handful of them back to back, so the re-reads hit L2.
+    // Tile order (TileIter).  V up to ~48 MB: any order, V stays in L2.  Larger: if there are enough query tiles to
+    // give every cluster a few items per ~16 MB image chunk, ALL clusters walk the same chunk at the same time —
+    // V is read from HBM once per pass whatever its size (cfg 4: 2.1 GB), and even at cfg 2 (67 MB, nominally
+    // L2-sized) the hot set shrinks from V + Q to one chunk + the query tiles (measured 3.34 -> 3.17 ms).
+    // Otherwise (retrieval: one or a few query tiles against a huge gallery) each cluster keeps to its own images
+    // and runs all query tiles against a handful of them back to back, so the re-reads hit L2.
     const size_t img_bytes = (size_t)Nv * D * 2;
     const size_t v_bytes = (size_t)Bv * img_bytes;
     int n_clusters = sms / cta_group;
-    p.C = (v_bytes <= (size_t)48 << 20) ? Bv : (Bv < 64 ? Bv : 64);
+    p.C = Bv;
     p.sync = 0;
-    if (v_bytes > (size_t)96 << 20) {
-        size_t c32 = ((size_t)32 << 20) / img_bytes;
-        if (c32 < 1) c32 = 1;
-        if ((size_t)n_m * c32 >= (size_t)4 * n_clusters) {
-            p.C = (int)(c32 > (size_t)Bv ? (size_t)Bv : c32);
+    if (v_bytes > (size_t)48 << 20) {
+        size_t c16 = ((size_t)16 << 20) / img_bytes;
+        if (c16 < 1) c16 = 1;
+        if ((size_t)n_m * c16 >= (size_t)4 * n_clusters) {
+            p.C = (int)(c16 > (size_t)Bv ? (size_t)Bv : c16);
             p.sync = 1;
         } else {
             size_t c = ((size_t)48 << 20) / ((size_t)n_clusters * img_bytes);
             p.C = (int)(c < 1 ? 1 : (c > 64 ? 64 : c));
+            if (p.C > Bv) p.C = Bv;
         }
     }
     if (flags & TRIAD_FWD_SYNC_CHUNKS) { p.C = Bv < 3 ? Bv : 3; p.sync = 1; }     // tests: tiny chunks on small shapes

@@ -24,13 +24,18 @@ import torch.distributed as dist
 class CudaKernels:
     """The product binding: the C-ABI ops."""
 
+    #: set by row_scale(): a mask was given, so zero-weight rows are packed out of the bf16 forward / dq
+    packed = False
+
     def row_scale(self, mask, Bq, Nq, device):
         from . import ops
+        self.packed = mask is not None
         return ops.row_scale(mask, Bq, Nq, device)
 
     def maxmean_fwd(self, q, v, scale, T):
-        from . import ops
-        return ops.maxmean_fwd(q, v, scale, T, want_idx=True)
+        from . import _lib, ops
+        flags = _lib.FWD_PACK_ROWS if (self.packed and q.dtype == torch.bfloat16) else 0
+        return ops.maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
 
     def infonce_partial(self, clip_rows, B, row0):
         from . import ops
@@ -42,8 +47,10 @@ class CudaKernels:
 
     def maxmean_bwd(self, q, v, idx, g, clip, scale, T):
         from . import ops
+        from . import _lib
+        flags = _lib.BWD_PACK_ROWS if (self.packed and q.dtype == torch.bfloat16) else 0
         dq, dv, _ = ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True,
-                                    need_dT=False, dv_f32=True)
+                                    need_dT=False, dv_f32=True, flags=flags)
         return dq, dv
 
 
