@@ -64,12 +64,14 @@ template <> struct Pack<float> {
 };
 
 // one element: accumulates clamp^2 and dS*raw, returns dL/d(raw) = coef * clamp(S,lo,0) * [S >= lo] * T
-__device__ __forceinline__ float one(float raw, float Tv, float lo, float coefT, float coef, double& s2, double& sT,
+// (s2, sT are fp32 sums over ONE 16-byte vector; the caller adds them to its fp64 accumulators once per vector —
+//  an fp64 add per element would cost as much as the HBM stream itself)
+__device__ __forceinline__ float one(float raw, float Tv, float lo, float coefT, float& s2, float& sT,
                                      float s /* = scaled(raw) */) {
     const float n = fminf(fmaxf(s, lo), 0.f);
-    s2 += (double)n * (double)n;
+    s2 = fmaf(n, n, s2);
     const float pass = (s >= lo) ? n : 0.f;          // clamp's gradient is 1 on [lo, 0] (n == 0 beyond 0 anyway)
-    sT += (double)(coef * pass) * (double)raw;       // dS/dT = <q,v> = raw
+    sT = fmaf(pass, raw, sT);                        // dS/dT = <q,v> = raw; the constant coef is applied once per block
     return coefT * pass;
 }
 
@@ -83,18 +85,38 @@ nonneg_kernel(void* __restrict__ S, size_t n, const float* __restrict__ Tptr, fl
     double s2 = 0.0, sT = 0.0;
     char* base = reinterpret_cast<char*>(S);
     const size_t nvec = n / E;
-    for (size_t k = (size_t)blockIdx.x * kThreads + threadIdx.x; k < nvec; k += (size_t)gridDim.x * kThreads) {
-        float f[E], o[E];
+    // kUnroll independent 16-byte loads in flight per thread (a pure HBM stream: bytes in flight are the throughput)
+    constexpr int kUnroll = 4;
+    const size_t stride = (size_t)gridDim.x * kThreads;
+    size_t k = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    for (; k + (kUnroll - 1) * stride < nvec; k += kUnroll * stride) {
+        float f[kUnroll][E];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) Pack<T>::load(base + (k + u * stride) * E * sizeof(T), f[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            float o[E], a2 = 0.f, aT = 0.f;
+#pragma unroll
+            for (int c = 0; c < E; ++c) o[c] = one(f[u][c], Tv, lo, coefT, a2, aT, Pack<T>::scaled(f[u][c], Tv));
+            s2 += (double)a2; sT += (double)aT;
+            if (write_grad) Pack<T>::store(base + (k + u * stride) * E * sizeof(T), o);
+        }
+    }
+    for (; k < nvec; k += stride) {
+        float f[E], o[E], a2 = 0.f, aT = 0.f;
         Pack<T>::load(base + k * E * sizeof(T), f);
 #pragma unroll
-        for (int c = 0; c < E; ++c) o[c] = one(f[c], Tv, lo, coefT, coef, s2, sT, Pack<T>::scaled(f[c], Tv));
+        for (int c = 0; c < E; ++c) o[c] = one(f[c], Tv, lo, coefT, a2, aT, Pack<T>::scaled(f[c], Tv));
+        s2 += (double)a2; sT += (double)aT;
         if (write_grad) Pack<T>::store(base + k * E * sizeof(T), o);
     }
     // tail (n % E elements), handled by block 0
     if (blockIdx.x == 0) {
         for (size_t k = nvec * E + threadIdx.x; k < n; k += kThreads) {
             const float raw = Pack<T>::scalar(base + k * sizeof(T));
-            const float o = one(raw, Tv, lo, coefT, coef, s2, sT, Pack<T>::scaled(raw, Tv));
+            float a2 = 0.f, aT = 0.f;
+            const float o = one(raw, Tv, lo, coefT, a2, aT, Pack<T>::scaled(raw, Tv));
+            s2 += (double)a2; sT += (double)aT;
             if (write_grad) Pack<T>::put(base + k * sizeof(T), o);
         }
     }
@@ -107,7 +129,7 @@ nonneg_kernel(void* __restrict__ S, size_t n, const float* __restrict__ Tptr, fl
         double a = 0.0, b = 0.0;
         for (int w = 0; w < kThreads / 32; ++w) { a += r2[w]; b += rT[w]; }
         partials[2 * blockIdx.x] = a;
-        partials[2 * blockIdx.x + 1] = b;
+        partials[2 * blockIdx.x + 1] = b * (double)coef;
     }
 }
 

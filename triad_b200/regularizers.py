@@ -21,8 +21,9 @@ import torch
 from . import _lib, ops
 from ._lib import check
 
-#: bytes of one raw-similarity chunk (rows x images-in-chunk x Nv); 512 MB keeps the three GEMMs large
-CHUNK_BYTES = 512 << 20
+#: bytes of one raw-similarity chunk (rows x images-in-chunk x Nv).  2 GiB: the three GEMMs stay large and the
+#: fp32 accumulation of dQ across chunks (one extra pass over dQ per chunk) is paid 4x at the B=256 shape
+CHUNK_BYTES = 2 << 30
 
 
 def nonneg_chunk(S: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write_grad: bool,
