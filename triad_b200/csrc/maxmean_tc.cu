@@ -231,7 +231,9 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
     if (warp == 0) {
         // =============================== TMA producer ===================================
-        if (lane == 0) {
+        // (whole warp in the loop, one elected lane issues — see the MMA role)
+        {
+            const bool issuer = elect_one();
             // in a pair, every load signals the LEADER's barrier (the only MMA issuer waits there)
             const uint32_t q_full_sig = (kCtaGroup == 2) ? mapa(bar_q_full, 0) : bar_q_full;
             const uint32_t v_full_sig = (kCtaGroup == 2) ? mapa(bar_v_full, 0) : bar_v_full;
@@ -247,17 +249,20 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 }
                 for (int sb = 0; sb < n_sub && ok; ++sb) {
                     for (int kb = 0; kb < p.num_kb; ++kb) {
-                        if (new_m && sb == 0) {
+                        if (new_m && sb == 0 && issuer) {
                             if (is_leader) mbar_expect_tx(bar_q_full + 8 * kb, kQkbBytes * kCtaGroup);
                             tma_load_2d<kCtaGroup>(q_smem + kb * kQkbBytes, &tmap_q, q_full_sig + 8 * kb,
                                                    kb * kBlockK, t.m * kTileRows + (int)cta_rank * kBlockM);
                         }
                         ok = mbar_wait(bar_v_empty + 8 * stage, phase ^ 1, p.abort_flag, 2);
                         if (!ok) break;
-                        if (is_leader) mbar_expect_tx(bar_v_full + 8 * stage, v_tx_bytes * kCtaGroup);
-                        // patches beyond Nv (last sub-tile) are zero-filled by TMA and masked in the epilogue
-                        tma_load_3d<kCtaGroup>(v_smem + stage * kVStageBytes, &tmap_v, v_full_sig + 8 * stage,
-                                               kb * kBlockK, sb * kMaxN + (int)cta_rank * n_half, t.j);
+                        if (issuer) {
+                            if (is_leader) mbar_expect_tx(bar_v_full + 8 * stage, v_tx_bytes * kCtaGroup);
+                            // patches beyond Nv (last sub-tile) are zero-filled by TMA and masked in the epilogue
+                            tma_load_3d<kCtaGroup>(v_smem + stage * kVStageBytes, &tmap_v, v_full_sig + 8 * stage,
+                                                   kb * kBlockK, sb * kMaxN + (int)cta_rank * n_half, t.j);
+                        }
+                        __syncwarp();
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -266,8 +271,16 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     } else if (warp == 1) {
         // =============================== MMA issuer =====================================
-        if (lane == 0 && is_leader) {
+        // The whole warp walks the loop (warp-uniform control flow, so tile decoding, stage bookkeeping and the
+        // shared-memory descriptors stay in uniform registers); one elected lane issues the tcgen05 instructions.
+        // (With the loop under `if (lane == 0)` every MMA cost an ELECT + five R2UR.BROADCAST + a lane loop and
+        // the issuing thread, not the tensor pipe, set the pace: ncu showed it busy 85 % of the time.)
+        if (is_leader) {
+            const bool issuer = elect_one();
             const uint32_t idesc = make_idesc(kTileRows, p.n_umma);
+            const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t a_desc0 = make_smem_desc(q_smem);
+            const uint64_t b_desc0 = make_smem_desc(v_smem);
             int stage = 0; uint32_t phase = 0, qf_phase = 0; int prev_m = -1; uint32_t t_cnt = 0;
             bool ok = true;
             Tile t;
@@ -278,30 +291,36 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 ok = mbar_wait(bar_t_empty + 8 * acc, acc_phase ^ 1, p.abort_flag, 3);
                 if (!ok) break;
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kMaxN;
+                const uint32_t d_tmem = tmem0 + acc * kMaxN;
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     if (new_m && sb == 0) { ok = mbar_wait(bar_q_full + 8 * kb, qf_phase, p.abort_flag, 4); if (!ok) break; }
                     ok = mbar_wait(bar_v_full + 8 * stage, phase, p.abort_flag, 5);
                     if (!ok) break;
                     tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc(q_smem + kb * kQkbBytes);
-                    const uint64_t b_desc = make_smem_desc(v_smem + stage * kVStageBytes);
+                    // start-address field is (addr >> 4): whole k-blocks / stages are added to the base descriptors
+                    const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)kb * (kQkbBytes >> 4));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)stage * (uint32_t)(kVStageBytes >> 4));
+                    if (issuer) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-                        umma_bf16<kCtaGroup>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
+                            umma_bf16<kCtaGroup>(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        umma_commit<kCtaGroup>(bar_v_empty + 8 * stage);      // frees the V stage in both CTAs
                     }
-                    umma_commit<kCtaGroup>(bar_v_empty + 8 * stage);      // frees the V stage in both CTAs
+                    __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 if (!ok) break;
-                umma_commit<kCtaGroup>(bar_t_full + 8 * acc);            // accumulator ready (both CTAs)
+                if (issuer) umma_commit<kCtaGroup>(bar_t_full + 8 * acc);            // accumulator ready (both CTAs)
+                __syncwarp();
               }
                 if (!ok) break;
                 TileIter peek = it;
                 Tile tn;
                 const bool next_new_m = !peek.next(tn) || tn.m != t.m;
-                if (next_new_m) umma_commit<kCtaGroup>(bar_q_empty);     // query tile may be overwritten
+                if (next_new_m && issuer) umma_commit<kCtaGroup>(bar_q_empty);     // query tile may be overwritten
+                __syncwarp();
                 if (new_m) qf_phase ^= 1;
                 prev_m = t.m;
             }

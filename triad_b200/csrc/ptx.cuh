@@ -107,6 +107,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
             ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
+// One lane of a fully active warp (the lowest): lets a WHOLE warp run a role's loop with warp-uniform control
+// flow — descriptors and barrier addresses then live in uniform registers — while only this lane issues the
+// single-thread instructions (tcgen05.mma / tcgen05.commit / TMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // arrive on `bar` (same offset in every CTA of the pair) once all previously issued MMAs completed
 template <int kCtaGroup>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
