@@ -84,6 +84,20 @@ def test_argument_validation_without_gpu(lib):
     assert lib.triad_diag_ranks(null, 4, one, null) == E["arg"]
     assert lib.triad_similarity_matrix(one, one, one, 0, 1, 1, 8, one, null) == E["shape"]
     assert lib.triad_retrieve_scores(one, 4, one, 3, 8, 64, 1, one, 1, 2, one, one, 1 << 30, null) == E["arg"]   # direction
+    n = lib.triad_nonneg_chunk
+    assert n(null, 8, 1, one, -60.0, 1e-3, 1, one, one, 1 << 20, null) == E["arg"]
+    assert n(one, 0, 1, one, -60.0, 1e-3, 1, one, one, 1 << 20, null) == E["shape"]
+    assert n(one, 8, 1, one, 1.0, 1e-3, 1, one, one, 1 << 20, null) == E["arg"]           # lo must be negative
+    assert n(odd, 8, 1, one, -60.0, 1e-3, 1, one, one, 1 << 20, null) == E["align"]
+    assert n(one, 8, 1, one, -60.0, 1e-3, 1, one, one, 8, null) == E["ws"]
+    assert lib.triad_nonneg_workspace_bytes() > 0
+    # the packed (masked-query) forward needs room for the packed copy of q and the row maps
+    base = lib.triad_maxmean_fwd_workspace_bytes_ex(4, 4, 8, 16, 64, 1, 0)
+    assert base == lib.triad_maxmean_fwd_workspace_bytes(4, 4, 8, 16, 64, 1)
+    assert lib.triad_maxmean_fwd_workspace_bytes_ex(4, 4, 8, 16, 64, 1, 16) >= 4 * 8 * 64 * 2 + 256
+    assert lib.triad_maxmean_fwd_workspace_bytes_ex(4, 4, 8, 16, 64, 0, 16) == base      # fp32: never packed
+    assert f(one, one, one, one, 2, 2, 4, 8, 64, 1, one, null, one, base, 16, null) == E["ws"]   # PACK_ROWS needs more
+    assert isinstance(lib.triad_launch_count(), int)
 
 
 def test_product_has_no_oracle_or_cpu_fallback():

@@ -132,11 +132,13 @@ __device__ __forceinline__ Tile decode_tile(uint32_t L, int n_m, int Bv, int C) 
 }
 
 // The sequence of (m-tile, image) work items of one cluster; the three warp roles walk it in lockstep.
-//   sync == 0: one contiguous range of the chunk-major linearisation (V fits in L2: every cluster may be
-//              anywhere in V, and a cluster changes its query tile as rarely as possible);
+//   sync == 0: one contiguous range of the chunk-major linearisation (chunks of C images; C = 1..64 for a huge
+//              gallery with few query tiles, C = Bv when V is small) — a cluster keeps to its own images and
+//              changes its query tile as rarely as the chunking allows;
 //   sync == 1: every image chunk is cut into one range per cluster, so ALL clusters stream the SAME chunk of
 //              C images at the same time — V is then read from HBM once per pass over the chunk, whatever
 //              its total size (B = 8192: 2.1 GB), at the price of re-loading the (small) query tiles per chunk.
+// launch_maxmean_tc() picks the mode from the size of V and the number of query tiles.
 struct TileIter {
     uint32_t n_m, Bv, C, cid, ncl, sync;
     uint32_t L, Lend, j0, cl;
