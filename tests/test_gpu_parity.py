@@ -357,6 +357,31 @@ def test_masked_text_shape_cfg3_slice(pack, holes):
         assert torch.equal(got[kept], tok.argmax().cpu()[kept])
 
 
+def test_dv_many_row_groups():
+    """More than 32 sort groups per query block (narrow D, many rows): the grouped dv gather refills its
+    lane-resident segment table; result must equal the global-sort path bit for bit."""
+    from triad_b200 import _lib, ops
+    Bq, Bv, Nq, Nv, D = 1100, 4, 250, 32, 64          # 275 000 rows = 34 groups of 8192
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = (torch.randn(Bq, Nq, D, generator=g, device="cuda") / D ** 0.5).bfloat16()
+    v = (torch.randn(Bv, Nv, D, generator=g, device="cuda") / D ** 0.5).bfloat16()
+    scale = ops.row_scale(None, Bq, Nq, q.device)
+    Tt = torch.tensor(1.5, device="cuda")
+    clip, idx = ops.maxmean_fwd(q, v, scale, Tt)
+    gw = torch.randn(Bq, Bv, generator=g, device="cuda")
+    _, dv_a, _ = ops.maxmean_bwd(q, v, idx, gw, clip, scale, Tt, need_dq=False, need_dT=False, dv_f32=True)
+    _, dv_b, _ = ops.maxmean_bwd(q, v, idx, gw, clip, scale, Tt, need_dq=False, need_dT=False, dv_f32=True,
+                                 flags=_lib.BWD_GENERIC_DV)
+    assert torch.equal(dv_a, dv_b)
+    # and against a direct fp64 evaluation of the scatter
+    idx_ref = ops.idx_to_reference_layout(idx, Bq, Nq)                       # (Bq,Bv,Nq)
+    w = (gw.double()[:, :, None] * scale.view(Bq, 1, Nq).double() * 1.5)    # (Bq,Bv,Nq)
+    ref = torch.zeros(Bv, Nv, D, dtype=torch.float64, device="cuda")
+    for j in range(Bv):
+        ref[j].index_add_(0, idx_ref[:, j].reshape(-1), (w[:, j].reshape(-1, 1) * q.double().view(-1, D)))
+    assert rel_err(dv_a.double().cpu(), ref.cpu()) < 1e-5
+
+
 @pytest.mark.parametrize("masked", [False, True])
 def test_sharded_step_single_rank_cuda(masked):
     """triad_b200.dist.sharded_contrastive_step with the product (CUDA) kernels on one rank — the code every
