@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Randomised shape sweep of the CUDA path against the CPU oracle (closed-form step): odd token / patch
+counts, every D the tcgen05 kernel accepts, ragged and non-prefix masks, Bq != multiples of anything.
+
+    python tools/fuzz_gpu.py [n_cases=40] [seed=0]
+"""
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import triad_b200  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def run_cases(n, seed, verbose=True):
+    """Returns (worst relative errors, list of failing case descriptions)."""
+    rng = random.Random(seed)
+    worst, failures = {}, []
+    for case in range(n):
+        B = rng.choice([1, 2, 3, 5, 8, 13, 24])
+        Nq = rng.choice([1, 2, 7, 16, 31, 33, 50, 77, 100, 250, 300])
+        Nv = rng.choice([1, 5, 16, 17, 100, 173, 255, 256, 257, 300, 513])
+        D = rng.choice([64, 128, 192, 256, 320, 512])
+        masked = rng.random() < 0.5
+        T = rng.choice([1.2, 1.5, 2.0])
+        q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=1000 + case, masked=masked, min_len=1)
+        if masked and rng.random() < 0.5 and Nq > 3:
+            mask[rng.randrange(B), rng.randrange(Nq)] = 0            # a hole: masks need not be prefixes
+        ref = O.contrastive_step_closed_form(q, v, T, mask)
+        m = triad_b200.TriadHotPath(temperature=T).cuda()
+        m.triad_regularizers = False
+        qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+        if masked:
+            clip, tok = m.compute_all_similarities_tv(qd, vd, mask.cuda())
+            loss = m.compute_contrastive_loss_tv(clip, tok)[0]
+        else:
+            clip, tok = m.compute_all_similarities_av(qd, vd)
+            loss = m.compute_contrastive_loss_av(clip, tok)[1]
+        loss.backward()
+        torch.cuda.synchronize()
+        idx = tok.argmax().cpu()
+        n_bad = int((idx != ref["idx"]).sum())
+        errs = {"clip": rel(tok.clip.detach().cpu(), ref["clip"]), "loss": abs(loss.item() - ref["loss"].item()) / max(abs(ref["loss"].item()), 1e-9),
+                "dq": rel(qd.grad.cpu(), ref["dq"]), "dv": rel(vd.grad.cpu(), ref["dv"])}
+        ok = n_bad <= max(2, 1e-3 * idx.numel()) and errs["clip"] < 1e-4 and errs["loss"] < 1e-4 and errs["dq"] < 6e-3 and errs["dv"] < 6e-3
+        if masked and bool((mask == 0).any()):
+            ok = ok and qd.grad[mask.cuda() == 0].abs().max().item() == 0.0
+        line = (f"{'ok  ' if ok else 'FAIL'} B={B} Nq={Nq} Nv={Nv} D={D} masked={masked} T={T} idx_mismatch={n_bad} "
+                + " ".join(f"{k}={e:.1e}" for k, e in errs.items()))
+        if verbose:
+            print(line, flush=True)
+        for k, e in errs.items():
+            worst[k] = max(worst.get(k, 0.0), e)
+        if not ok:
+            failures.append(line)
+    return worst, failures
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    worst, failures = run_cases(n, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    print("worst:", {k: f"{e:.2e}" for k, e in worst.items()})
+    if failures:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
