@@ -211,6 +211,12 @@ bool dq_tile_supported(int D, int dtype) { return dtype == TRIAD_DTYPE_BF16 && D
 namespace dq3 {
 using namespace ptx;
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 u;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+    return u;
+}
+
 constexpr int kRows = 512;
 constexpr int kThreads = 512;
 constexpr int kSlice = 64;
@@ -264,6 +270,7 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
     for (int k = 0; k < 8; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[k][e] = make_float2(0.f, 0.f);
+    const uint32_t vs_base = sbase + (uint32_t)c * 16u;
 
     // staging is split in two so the global loads of group G+1 are in flight while group G computes
     uint8_t pi[kJG];
@@ -326,10 +333,12 @@ dq_smem_kernel(const __grid_constant__ CUtensorMap tmap_v, const uint8_t* __rest
                     const float4 wa = *reinterpret_cast<const float4*>(&w_s[st][jj][rb]);
                     const float4 wb = *reinterpret_cast<const float4*>(&w_s[st][jj][rb + 4]);
                     const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                    const unsigned char* vs = v_s + vslot * kVStageBytes + c * 16;
+                    // shared-space addresses (32-bit) computed from a base hoisted out of the loop: a generic-pointer
+                    // dereference made ptxas rebuild the shared window base (S2R/LEA/LOP chain) for every image
+                    const uint32_t vs = vs_base + (uint32_t)vslot * kVStageBytes;
                     uint4 d[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) d[k] = *reinterpret_cast<const uint4*>(vs + off[k]);
+                    for (int k = 0; k < 8; ++k) d[k] = lds128(vs + off[k]);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) dq2::fma8p(acc[k], w[k], d[k]);
                     __syncwarp();
