@@ -375,6 +375,34 @@ def run_triad(args, cfg_key):
                         "pressure through 3 library GEMMs per image chunk + triad_nonneg_chunk, smoothness / sparsity on "
                         "the positive pairs; not part of BASELINE.json's metric"}
 
+    # ---- single-GPU rate at the multi-GPU workload's per-rank shape (the strong-scaling denominator) ----------
+    # N > 1 runs cfg 4 (B = 8192); one GPU's share of that at 8 ranks is 1024 queries x 8192 images.  Timing that
+    # shape here gives the per-GPU rate the N-GPU numbers should be compared with (cfg 2's B = 256 step is short
+    # enough to run at boost clocks; 0.8 s of continuous tensor work runs under the power cap).
+    rank_shape = None
+    if world == 1 and cfg_key == "cfg2" and not args.no_rank_shape:
+        c4 = CONFIGS["cfg4"]
+        Bq4, Bv4 = c4["B"] // 8, c4["B"]
+        (q4, _, _), = make_device_inputs(c4, Bq4, 99, dev, 1)
+        (_, v4, _), = make_device_inputs(c4, Bv4, 98, dev, 1)
+        T4 = torch.tensor(1.5, device=dev)
+        ck = CudaKernels()
+
+        def rank_step():
+            sc = ck.row_scale(None, Bq4, c4["Nq"], dev)
+            clip4, idx4 = ck.maxmean_fwd(q4, v4, sc, T4)
+            lse4, cp4 = ck.infonce_partial(clip4, Bv4, 0)
+            g4, _ = ck.infonce_finish(clip4, Bv4, 0, lse4, cp4.reshape(1, 2, Bv4))
+            return ck.maxmean_bwd(q4, v4, idx4, g4, clip4, sc, T4)
+
+        rank_step()
+        rs_ms = timed(lambda i: rank_step(), 2)
+        rank_shape = {"workload": f"one rank's share of cfg4 at 8 GPUs: {Bq4} queries x {Bv4} images, fwd + InfoNCE block + bwd, "
+                                  "no collectives", "ms_per_step": rs_ms, "value": float(Bq4) * Bv4 / (rs_ms * 1e-3),
+                      "unit": "clip-pairs/s per GPU"}
+        del q4, v4
+        torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel (tcgen05 forward) ---------------------------------------
     peak, peak_sustained, peak_src = measured_peaks()
     roof = None
@@ -413,6 +441,8 @@ def run_triad(args, cfg_key):
         }
         if full is not None:
             out["full_loss"] = full
+        if rank_shape is not None:
+            out["cfg4_rank_shape_1gpu"] = rank_shape
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_seconds)
         print(json.dumps(out), flush=True)
@@ -430,6 +460,7 @@ def main():
     ap.add_argument("--impl", default="triad", choices=["triad", "reference"])
     ap.add_argument("--config", default="auto", choices=["auto"] + list(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rank-shape", action="store_true", help="skip the cfg4 per-rank-shape timing at N=1")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -54,3 +54,17 @@ class OracleKernels:
         idx_ref = idx.to(torch.int64).view(Bv, Bq, pad)[:, :, :Nq].permute(1, 0, 2)
         dq, dv, _ = O.maxmean_backward(q, v, idx_ref, g, float(T), scale.view(Bq, Nq), clip)
         return dq.to(q.dtype), dv.float()
+
+
+class PipelinedOracleKernels(OracleKernels):
+    """Adds the split dv / dq entry points, so the sharded step takes its pipelined (per-destination reduce) path."""
+
+    def maxmean_bwd_dv(self, q, v, idx, g, scale, T):
+        Bq, Nq, D = q.shape
+        clip = torch.zeros(Bq, v.shape[0])
+        return self.maxmean_bwd(q, v, idx, g, clip, scale, T)[1]
+
+    def maxmean_bwd_dq(self, q, v, idx, g, scale, T):
+        Bq = q.shape[0]
+        clip = torch.zeros(Bq, v.shape[0])
+        return self.maxmean_bwd(q, v, idx, g, clip, scale, T)[0]

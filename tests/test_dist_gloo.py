@@ -21,19 +21,19 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, masked, ret):
+def _worker(rank, world, port, masked, ret, pipelined=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from tests.cpu_kernels import OracleKernels
+        from tests.cpu_kernels import OracleKernels, PipelinedOracleKernels
         from triad_b200.dist import sharded_contrastive_step, stats_from_all_sums
         B, Nq, Nv, D = 6, 9, 20, 16
         q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.float32, seed=4, masked=masked)
         Bl = B // world
         sl = slice(rank * Bl, (rank + 1) * Bl)
         out = sharded_contrastive_step(q[sl], v[sl], torch.tensor(1.5), mask[sl] if masked else None,
-                                       kernels=OracleKernels())
+                                       kernels=PipelinedOracleKernels() if pipelined else OracleKernels())
         stats = stats_from_all_sums(out["all_sums"], B, "av")
         ret[rank] = {"loss": out["loss"].item(), "dq": out["dq"], "dv": out["dv"], "dT": out["dT"].item(),
                      "stats": stats}
@@ -41,12 +41,15 @@ def _worker(rank, world, port, masked, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
 @pytest.mark.parametrize("masked", [False, True])
-def test_two_rank_step_matches_full_batch(masked):
+def test_two_rank_step_matches_full_batch(masked, pipelined):
+    """pipelined=False: one reduce-scatter of the dv partial (kernels without the split entry points);
+    pipelined=True: the product path — per-destination reduces overlapped with the next dv chunk and dq."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), masked, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), masked, ret, pipelined), nprocs=world, join=True)
     B, Nq, Nv, D = 6, 9, 20, 16
     q, v, mask = O.make_inputs(B, Nq, Nv, D, torch.float32, seed=4, masked=masked)
     ref = O.contrastive_step_closed_form(q, v, 1.5, mask)

@@ -6,7 +6,8 @@ queries and images [r*Bl,(r+1)*Bl).  One exchange each way:
   forward   all-gather(V)                     -> every rank scores its queries against ALL images
             all-gather(column (max,sumexp))   -> 2*B floats per rank, completes the column softmax
             all-gather(8 fp64 sums)           -> loss and the similarity statistics
-  backward  reduce-scatter(dV partial, fp32)  -> each rank receives the gradient of its own images
+  backward  reduce(dV partial, fp32), one destination rank at a time, pipelined with the dV gather of the next
+            rank's images and with dQ  -> each rank receives the gradient of its own images
             (dQ is local; dT is a sum of the per-rank  sum g*clip  already in the 8 sums)
 
 There is no other data-path collective; per-rank work is (B/W) x B pairs.  Collectives go through
@@ -52,6 +53,19 @@ class CudaKernels:
         dq, dv, _ = ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True,
                                     need_dT=False, dv_f32=True, flags=flags)
         return dq, dv
+
+
+    # dv / dq separately: lets the sharded step reduce one destination rank's dv while the next one is computed
+    def maxmean_bwd_dv(self, q, v, idx, g, scale, T):
+        from . import ops
+        _, dv, _ = ops.maxmean_bwd(q, v, idx, g, None, scale, T, need_dq=False, need_dv=True, need_dT=False, dv_f32=True)
+        return dv
+
+    def maxmean_bwd_dq(self, q, v, idx, g, scale, T):
+        from . import _lib, ops
+        flags = _lib.BWD_PACK_ROWS if (self.packed and q.dtype == torch.bfloat16) else 0
+        dq, _, _ = ops.maxmean_bwd(q, v, idx, g, None, scale, T, need_dq=True, need_dv=False, need_dT=False, flags=flags)
+        return dq
 
 
 def _all_gather(x: torch.Tensor, W: int, group) -> torch.Tensor:
@@ -115,8 +129,24 @@ def sharded_contrastive_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
     if not need_grads:
         return out
 
-    dq, dv_partial = k.maxmean_bwd(q_local, v_all, idx, g, clip_rows, scale, T)   # dv_partial (B,Nv,D) fp32
-    dv32 = _reduce_scatter_rows(dv_partial, W, r, group) if W > 1 else dv_partial
+    if W > 1 and hasattr(k, "maxmean_bwd_dv"):
+        # Pipelined: the fp32 dv partial of ONE destination rank's images at a time; its reduction to that rank
+        # travels (NCCL's stream) while the next rank's images are gathered for, and dq — which needs no
+        # communication — runs under the last reductions.  Same sums as one reduce-scatter of the whole partial.
+        works, dv32 = [], None
+        for d in range(W):
+            sl = slice(d * Bl, (d + 1) * Bl)
+            part = k.maxmean_bwd_dv(q_local, v_all[sl], idx[sl], g[:, sl].contiguous(), scale, T)   # (Bl,Nv,D) fp32
+            dst = dist.get_global_rank(group, d) if group is not None else d
+            works.append(dist.reduce(part, dst=dst, op=dist.ReduceOp.SUM, group=group, async_op=True))
+            if d == r:
+                dv32 = part
+        dq = k.maxmean_bwd_dq(q_local, v_all, idx, g, scale, T)
+        for w in works:
+            w.wait()
+    else:
+        dq, dv_partial = k.maxmean_bwd(q_local, v_all, idx, g, clip_rows, scale, T)   # dv_partial (B,Nv,D) fp32
+        dv32 = _reduce_scatter_rows(dv_partial, W, r, group) if W > 1 else dv_partial
     out["dq"] = dq
     out["dv"] = dv32.to(v_local.dtype)
     out["dT"] = (all_sums[:, 6].sum() / T.double()).to(torch.float32)
