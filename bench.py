@@ -372,8 +372,8 @@ def run_triad(args, cfg_key):
         model.triad_regularizers = False
         full = {"value": float(B) * B / (full_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": full_ms, "steps": k_full,
                 "what": "same step with the reference's regularisers on (model.py:394-428 / :516-542): dense non-negative "
-                        "pressure through 3 library GEMMs per image chunk + triad_nonneg_chunk, smoothness / sparsity on "
-                        "the positive pairs; not part of BASELINE.json's metric"}
+                        "pressure (tcgen05 forward in dense-regulariser mode + 2 library GEMMs per image chunk), smoothness / "
+                        "sparsity on the positive pairs; not part of BASELINE.json's metric"}
 
     # ---- single-GPU rate at the multi-GPU workload's per-rank shape (the strong-scaling denominator) ----------
     # N > 1 runs cfg 4 (B = 8192); one GPU's share of that at 8 ranks is 1024 queries x 8192 images.  Timing that

@@ -154,6 +154,16 @@ size_t triad_nonneg_workspace_bytes(void);
 int triad_nonneg_chunk(void* S, size_t n, int dtype, const float* temperature, float lo, float coef,
                        int write_grad, double* sums, void* ws, size_t ws_bytes, void* stream);
 
+/* The same for bf16 embeddings straight from q and a block of images (D % 64 == 0, D <= 512, Nv <= 256,
+ * Nv % 8 == 0): the tcgen05 forward kernel computes the similarities and its epilogue writes
+ * n_out[r][j*Nv + p] = dL/d<q_r, v_jp> (bf16, row pitch ldn >= Bv*Nv elements, ldn % 8 == 0) when write_grad != 0,
+ * accumulating sums[0..1] as above — no S chunk is materialised and there is no separate elementwise pass. */
+size_t triad_nonneg_fused_workspace_bytes(void);
+int triad_nonneg_fused_chunk(const void* q, const void* v, const float* temperature,
+                             int Bq, int Bv, int Nq, int Nv, int D, float lo, float coef,
+                             void* n_out, long long ldn, int write_grad, double* sums,
+                             void* ws, size_t ws_bytes, void* stream);
+
 /* ---- retrieval: one query against a gallery, top-k ---------------------------------- */
 /* Replaces the per-pair aggregators retrieval.py:106-110 / :190-193 (direction 0:
  * mean_q max_p) and :112-115 / :195-198 (direction 1: mean_p max_q) and the python double

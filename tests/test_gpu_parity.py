@@ -115,11 +115,12 @@ def _near_tie_report(q, v, T, idx_a, idx_b):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
-@pytest.mark.parametrize("chunk_bytes", [None, 1 << 14])
-def test_golden_total_loss_with_regularisers(case, chunk_bytes, monkeypatch):
+@pytest.mark.parametrize("chunk_bytes,fused", [(None, True), (1 << 14, True), (None, False)])
+def test_golden_total_loss_with_regularisers(case, chunk_bytes, fused, monkeypatch):
     """total loss, regulariser values and the gradients of the TOTAL loss (dense
     non-negative pressure + positive-pair terms on top of the contrastive part) vs the reference."""
     from triad_b200 import regularizers as R
+    monkeypatch.setattr(R, "USE_FUSED", fused)        # tcgen05 forward writing N vs library GEMM + elementwise kernel
     if chunk_bytes is not None:                       # many small image chunks: exercises the chunk loop
         monkeypatch.setattr(R, "CHUNK_BYTES", chunk_bytes)
     gold = load_golden(case.name)

@@ -115,7 +115,7 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
         if (idx) TRIAD_CUDA_CHECK(cudaMemsetAsync(idx, 0, (size_t)Bv * Bq * nq_padded(Nq) * (Nv > 256 ? 2 : 1), st));
         const int cta_group = (flags & TRIAD_FWD_FORCE_1CTA) ? 1 : 2;
         rc = launch_maxmean_tc(qp, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags,
-                               (const int*)maps, st);
+                               (const int*)maps, nullptr, st);
         if (rc) return rc;
         return launch_finalize_clip_packed(part, (const int*)maps, Bq, Bv, Nq, clip, st);
     }
@@ -124,7 +124,7 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
         // spend a 256-row MMA on <= 128 rows, and at one tile per image that MMA time equals the HBM time of
         // the image, leaving no slack to overlap; alone, each SM streams its own images at twice that rate.
         const int cta_group = ((flags & TRIAD_FWD_FORCE_1CTA) || M <= 128) ? 1 : 2;
-        rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags, nullptr, st);
+        rc = launch_maxmean_tc(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags, nullptr, nullptr, st);
     } else {
         rc = launch_maxmean_simt(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, dtype, part, idx, st);
     }

@@ -56,10 +56,13 @@ int launch_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, cuda
 int launch_maxmean_simt(const void* q, const void* v, const float* row_scale, const float* T,
                         int inv_T, int M, int Bv, int Nq, int Nv, int D, int dtype,
                         float* part, void* idx, cudaStream_t st);   // idx: [Bv][M/Nq][nq_padded(Nq)]
+// dense-regulariser mode of the tcgen05 forward (maxmean_tc.cu, kEmitN): instead of reducing each tile the
+// epilogue writes N = dL/d<q,v> of the non-negative-pressure term; partials: [SMs*8][2] doubles
+struct EmitNArgs { void* n_out; long long ldn; float lo, coef; int write_n; double* partials; };
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
                       float* part, void* idx, int* abort_flag, int cta_group, int flags, const int* pack_maps,
-                      cudaStream_t st);
+                      const EmitNArgs* emit, cudaStream_t st);
 int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
 // packed rows (pack.cu): maps = off[Bq+1] | rowmap[Bq*Nq] | scratch
 size_t pack_map_bytes(int Bq, int Nq);

@@ -74,6 +74,13 @@ struct Params {
     const int* rowmap;
     int Bq;
     int pieces;              // packed partial layout: part[(j*Bq + i)*pieces + (group - first group of query i)]
+    // kEmitN (dense regulariser, dense_reg.cu): the epilogue writes N = dL/d<q,v> of the non-negative pressure
+    // term for every (row, patch) instead of reducing the tile
+    __nv_bfloat16* n_out;    // [M][ldn] bf16; image j of this call occupies columns [j*Nv, (j+1)*Nv)
+    long long ldn;
+    float lo, coef;          // clamp floor (< 0), 2*weight/numel
+    int write_n;             // 0: value only
+    double* n_partials;      // [gridDim.x*4][2]: sum clamp^2, sum dS*<q,v> per epilogue warp
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -110,6 +117,72 @@ __device__ __forceinline__ void first_ge32(const uint32_t (&r)[32], int col0, in
     }
     const int lo = min(min(b[0], b[1]), min(b[2], b[3]));
     if (lo < min(lim, 32)) best = col0 + lo;            // 64 = "none"; columns >= lim are padding
+}
+
+// dense-regulariser epilogue, one 32-column chunk of the warp's 32 rows: o = coefT*min(T*acc, 0) as bf16, sum of
+// min(.)^2 and the row minimum (to detect the clamp floor) in four independent chains.  A thread owns a ROW of
+// the accumulator, so storing straight from registers would hit 32 different rows per store instruction (32
+// half-filled sectors); the 32 x 64-byte block is instead transposed through a small shared-memory staging area
+// (16 columns at a time, row pitch 48 bytes: conflict-free for both phases) and leaves as 16 rows x one full
+// 32-byte sector per instruction.
+// Columns >= Nv contribute nothing and are not stored (Nv % 8 == 0: whole 16-byte pieces).
+constexpr uint32_t kStgPitch = 48;                                  // bytes per staged row (16 columns = 32 bytes, + 16)
+constexpr uint32_t kStgBytesPerWarp = 32 * kStgPitch;               // 1536 (8 epilogue warps: 12 KB, inside one ring stage)
+constexpr int kEmitEpiWarps = 8;                                    // two per scheduler: columns [0,128) and [128,256)
+constexpr int kEmitThreads = (kEpiWarp0 + kEmitEpiWarps) * 32;      // 384
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 u;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+    return u;
+}
+
+template <bool kFull>
+__device__ __forceinline__ void emit_chunk_fast_t(const uint32_t (&r)[32], int col0, int Nv, float Tval, float coefT,
+                                                  float (&a2)[4], float (&mn)[4], bool store, uint32_t stg, int lane,
+                                                  __nv_bfloat16* nblock /* &N[warp's first row][image's first column] */,
+                                                  long long ldn, int rows_valid) {
+    uint32_t packed[16];
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+        float s0 = __uint_as_float(r[e]) * Tval, s1 = __uint_as_float(r[e + 1]) * Tval;
+        if constexpr (!kFull) { if (col0 + e >= Nv) s0 = 0.f; if (col0 + e + 1 >= Nv) s1 = 0.f; }
+        const float n0 = fminf(s0, 0.f), n1 = fminf(s1, 0.f);
+        const int k = (e >> 1) & 3;
+        a2[k] = fmaf(n0, n0, a2[k]);
+        a2[k] = fmaf(n1, n1, a2[k]);
+        mn[k] = fminf(mn[k], fminf(s0, s1));
+        __nv_bfloat162 hh = __floats2bfloat162_rn(n0 * coefT, n1 * coefT);
+        packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    if (!store) return;                                             // warp-uniform (write_n)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                                   // two 16-column halves of the chunk
+        sts128(stg + lane * kStgPitch, packed[8 * h], packed[8 * h + 1], packed[8 * h + 2], packed[8 * h + 3]);
+        sts128(stg + lane * kStgPitch + 16, packed[8 * h + 4], packed[8 * h + 5], packed[8 * h + 6], packed[8 * h + 7]);
+        __syncwarp();
+        const int piece = lane & 1;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int row = 16 * i + (lane >> 1);
+            const uint4 u = lds128(stg + row * kStgPitch + 16 * piece);
+            const int col = col0 + 16 * h + 8 * piece;
+            // streaming store: N (gigabytes per call) must not evict the V chunk and the query tiles from L2
+            if (row < rows_valid && col < Nv) __stcs(reinterpret_cast<uint4*>(nblock + (size_t)row * (size_t)ldn + col), u);
+        }
+        __syncwarp();
+    }
+}
+// the per-column mask of the last, partial chunk costs an ISETP + FSEL per element: only that chunk pays for it
+__device__ __forceinline__ void emit_chunk_fast(const uint32_t (&r)[32], int col0, int Nv, float Tval, float coefT,
+                                                float (&a2)[4], float (&mn)[4], bool store, uint32_t stg, int lane,
+                                                __nv_bfloat16* nblock, long long ldn, int rows_valid) {
+    if (col0 >= Nv) return;                                         // warp-uniform
+    if (col0 + 32 <= Nv) emit_chunk_fast_t<true>(r, col0, Nv, Tval, coefT, a2, mn, store, stg, lane, nblock, ldn, rows_valid);
+    else emit_chunk_fast_t<false>(r, col0, Nv, Tval, coefT, a2, mn, store, stg, lane, nblock, ldn, rows_valid);
 }
 
 struct Tile { int m, j; };
@@ -175,12 +248,13 @@ struct TileIter {
 // ---------------------------------------------------------------------------------------------
 // kSub = false: one accumulator tile per image (Nv <= 256), the training shapes' hot path;
 // kSub = true : n_sub 256-patch sub-tiles per image.
-template <int kCtaGroup, bool kSub>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kCtaGroup, bool kSub, bool kEmitN = false>
+__global__ void __launch_bounds__(kEmitN ? kEmitThreads : kThreads, 1)
 maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
                   const Params p) {
     constexpr int kVStageBytes = (kMaxN / kCtaGroup) * kBlockK * 2;       // 32 KB / 16 KB
-    constexpr int kStages = kVRingBytes / kVStageBytes;                   // 3 / 6
+    // dense-regulariser mode gives the last ring stage (>= 16 KB) to the epilogue's store staging (4 x 2560 B)
+    constexpr int kStages = kVRingBytes / kVStageBytes - (kEmitN ? 1 : 0);   // 3 / 6  (2 / 5)
     constexpr int kTileRows = kBlockM * kCtaGroup;
 
     extern __shared__ uint8_t smem_raw[];
@@ -222,7 +296,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int i = 0; i < kMaxKB; ++i) mbar_init(bar_q_full + 8 * i, 1);
         mbar_init(bar_q_empty, 1);
         for (int i = 0; i < kStages; ++i) { mbar_init(bar_v_full + 8 * i, 1); mbar_init(bar_v_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_t_full + 8 * i, 1); mbar_init(bar_t_empty + 8 * i, 4 * kCtaGroup); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_t_full + 8 * i, 1); mbar_init(bar_t_empty + 8 * i, (kEmitN ? kEmitEpiWarps : 4) * kCtaGroup); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
@@ -326,6 +400,108 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if (new_m) qf_phase ^= 1;
                 prev_m = t.m;
             }
+        }
+    } else if (warp >= kEpiWarp0 && kEmitN) {
+        // ============ epilogue, dense-regulariser mode: N = coef*T*min(S,0) for every pair =============
+        // One pass over the accumulator: s = T*acc, n = min(s, 0); the tile's sum of n^2 feeds the value and,
+        // because n*s == n^2, also dL/dT (sum dS*<q,v> = sum n^2 / T).  The clamp floor `lo` (-60 / -20) is far
+        // outside the data range; a tile that does reach it (row minimum < lo) is redone exactly before its
+        // accumulator is released.  Padded text tokens take part, as in the reference (model.py:525).
+        const int quarter = warp & 3;
+        const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
+        const float Tval = *p.T;
+        const float coefT = p.coef * Tval;
+        const int half = (warp - kEpiWarp0) >> 2;                  // 0: columns [0,128), 1: [128,256)
+        const uint32_t stg = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0) * kStgBytesPerWarp;
+        double s2 = 0.0, sT = 0.0;
+        uint32_t t_cnt = 0;
+        bool alive = true;
+        Tile t;
+        constexpr int kCh = kMaxN / 32 / 2;                         // 32-column chunks per warp
+        const int cbase = half * kCh;
+        while (alive && it.next(t)) {
+            const int wrow0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;      // the warp's first row
+            const int r = wrow0 + lane;
+            const bool vrow = r < p.M;
+            const int rows_valid = max(0, min(32, p.M - wrow0));
+            __nv_bfloat16* nblock = p.n_out + (size_t)min(wrow0, p.M - 1) * (size_t)p.ldn + (size_t)t.j * p.Nv;
+            __nv_bfloat16* nrow = nblock + (size_t)(vrow ? lane : 0) * (size_t)p.ldn;
+            const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
+            ++t_cnt;
+            bool ok = mbar_wait(bar_t_full + 8 * acc, acc_phase, p.abort_flag, 6);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) { alive = false; break; }
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxN;
+            // ---- fast pass: pipelined 32-column loads (chunk c+1 in flight while chunk c is processed), four
+            //      independent accumulator chains per chunk ----
+            float a2[4] = {0.f, 0.f, 0.f, 0.f}, mn[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                uint32_t bufA[32], bufB[32];
+                tmem_ld32_raw(taddr + cbase * 32, bufA);
+                tmem_wait_ld();
+#pragma unroll
+                for (int cc = 0; cc < kCh; cc += 2) {
+                    const int c = cbase + cc;
+                    tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
+                    emit_chunk_fast(bufA, c * 32, p.Nv, Tval, coefT, a2, mn, p.write_n != 0, stg, lane, nblock, p.ldn, rows_valid);
+                    tmem_wait_ld();
+                    if (cc + 2 < kCh) tmem_ld32_raw(taddr + (c + 2) * 32, bufA);         // compile-time condition
+                    emit_chunk_fast(bufB, (c + 1) * 32, p.Nv, Tval, coefT, a2, mn, p.write_n != 0, stg, lane, nblock, p.ldn, rows_valid);
+                    tmem_wait_ld();
+                }
+            }
+            const float a2s = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+            const float mns = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
+            if (!__any_sync(0xffffffffu, vrow && mns < p.lo)) {
+                if (vrow) { s2 += (double)a2s; sT += (double)a2s / (double)Tval; }
+            } else {
+                // ---- exact pass (some similarity of this warp's rows is below the clamp floor): redo the tile with
+                //      the clamp and its gradient gate applied, overwriting what the fast pass stored ----
+                float e2 = 0.f, eT = 0.f;
+                for (int c = cbase; c < cbase + kCh; ++c) {
+                    if (c * 32 >= p.Nv) break;                               // warp-uniform
+                    uint32_t buf[32];
+                    tmem_ld32_raw(taddr + c * 32, buf);
+                    tmem_wait_ld();
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float o[2];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float raw = __uint_as_float(buf[e + h]);
+                            const float sv = (c * 32 + e + h < p.Nv) ? raw * Tval : 0.f;
+                            const float n = fminf(sv, 0.f);
+                            const float nc = fmaxf(n, p.lo);
+                            e2 = fmaf(nc, nc, e2);
+                            const float pass = (sv >= p.lo) ? n : 0.f;
+                            eT = fmaf(pass, raw, eT);
+                            o[h] = pass * coefT;
+                        }
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(o[0], o[1]);
+                        packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                    if (p.write_n && vrow) {
+                        for (int k = 0; k < 4 && c * 32 + 8 * k < p.Nv; ++k)
+                            *reinterpret_cast<uint4*>(nrow + c * 32 + 8 * k) =
+                                make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+                    }
+                }
+                if (vrow) { s2 += (double)e2; sT += (double)eT; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtaGroup == 2) mbar_arrive_cluster(t_empty_sig + 8 * acc);
+                else mbar_arrive_local(bar_t_empty + 8 * acc);
+            }
+        }
+        s2 = warp_sum_d(s2);
+        sT = warp_sum_d(sT);
+        if (lane == 0) {
+            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
+            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
         }
     } else if (warp >= kEpiWarp0) {
         // =============================== epilogue =======================================
@@ -475,9 +651,9 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
     return encode_tmap_bf16(map, base, rank, dims, strides, box, true);
 }
 
-template <int kCtaGroup, bool kSub>
+template <int kCtaGroup, bool kSub, bool kEmitN = false>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& p, int n_clusters, cudaStream_t st) {
-    auto kern = maxmean_tc_kernel<kCtaGroup, kSub>;
+    auto kern = maxmean_tc_kernel<kCtaGroup, kSub, kEmitN>;
     static bool attr_set = false;
     if (!attr_set) {
         TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -485,7 +661,7 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& 
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * kCtaGroup));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kEmitN ? kEmitThreads : kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -507,7 +683,7 @@ bool tc_supported(int Nv, int D) { return Nv >= 1 && Nv <= 65535 && D % tc::kBlo
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
                       float* part, void* idx, int* abort_flag, int cta_group, int flags, const int* pack_maps,
-                      cudaStream_t st) {
+                      const EmitNArgs* emit, cudaStream_t st) {
     using namespace tc;
     if (!tc_supported(Nv, D)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "tcgen05 forward: needs D in {64,...,512} (multiple of 64)");
     const int tile_rows = kBlockM * cta_group;
@@ -559,6 +735,12 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     p.pack_off = pack_maps;                                   // q then points at the PACKED rows
     p.rowmap = pack_maps ? pack_maps + p.Bq + 1 : nullptr;
     p.pieces = packed_pieces(Nq);
+    p.n_out = nullptr; p.ldn = 0; p.lo = 0.f; p.coef = 0.f; p.write_n = 0; p.n_partials = nullptr;
+    if (emit) {
+        if (n_sub > 1 || Nv % 8 != 0 || pack_maps) return fail_msg(TRIAD_ERR_UNSUPPORTED, "dense-regulariser forward: needs Nv <= 256, Nv % 8 == 0");
+        p.n_out = (__nv_bfloat16*)emit->n_out; p.ldn = emit->ldn; p.lo = emit->lo; p.coef = emit->coef;
+        p.write_n = emit->write_n; p.n_partials = emit->partials;
+    }
 
     CUtensorMap mq, mv;
     {
@@ -578,6 +760,11 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     const long long total = (long long)n_m * Bv;
     if ((long long)n_clusters > total) n_clusters = (int)total;
     if (n_clusters < 1) n_clusters = 1;
+    if (emit) {
+        // every CTA's four epilogue warps write a partial: clear the slots of CTAs that get no work
+        TRIAD_CUDA_CHECK(cudaMemsetAsync(emit->partials, 0, (size_t)sms * kEmitEpiWarps * 2 * sizeof(double), st));
+        return cta_group == 2 ? launch_t<2, false, true>(mq, mv, p, n_clusters, st) : launch_t<1, false, true>(mq, mv, p, n_clusters, st);
+    }
     if (n_sub > 1) return cta_group == 2 ? launch_t<2, true>(mq, mv, p, n_clusters, st) : launch_t<1, true>(mq, mv, p, n_clusters, st);
     return cta_group == 2 ? launch_t<2, false>(mq, mv, p, n_clusters, st) : launch_t<1, false>(mq, mv, p, n_clusters, st);
 }

@@ -5,11 +5,13 @@ Two kinds of term read the token-similarity tensor the fused path never builds:
 
 * ``l_nonneg = mean(clamp(S, lo, 0)^2)`` over ALL Bq*Bv*Nq*Nv pairs (model.py:411-412, lo=-60;
   :525-526, lo=-20).  Its gradient is dense (every negative similarity), so its backward is two
-  real GEMMs.  ``DenseNonNeg`` streams the batch in image chunks: library GEMM (raw <q,v> chunk,
-  bf16) -> ``triad_nonneg_chunk`` (csrc/dense_reg.cu: in place S -> dL/d<q,v>, fp64 reductions
-  for the value and dL/dT) -> two library GEMMs (dQ += N V, dV = N^T Q).  3 GEMM units, one
-  read+write of each S chunk; nothing of size B^2*Nq*Nv is ever resident (see DESIGN.md §4 K5 for
-  why this beats a fused tcgen05 backward at D = 512).
+  real GEMMs.  ``DenseNonNeg`` streams the batch in image chunks: N = dL/d<q,v> for the chunk comes
+  straight out of the tcgen05 forward kernel (``triad_nonneg_fused_chunk``: the epilogue writes
+  coef*T*min(S,0) instead of reducing the tile, and the sums for the value and dL/dT), then two
+  library GEMMs (dQ += N V, dV = N^T Q).  For fp32 inputs / shapes the tensor-core kernel does not
+  take: library GEMM (raw <q,v>) -> ``triad_nonneg_chunk`` (elementwise, in place) -> the same two
+  GEMMs.  Nothing of size B^2*Nq*Nv is ever resident (see DESIGN.md §4 K5 for why the two backward
+  GEMMs are not fused into a flash-attention-style kernel at D = 512).
 * terms on the B POSITIVE pairs only (token_sims[i,i]): temporal smoothness (model.py:394-408)
   and patch-usage sparsity (:528-541).  They touch B*Nq*Nv elements — 1/B of the tensor — and are
   written with the reference's own ATen ops on a batched GEMM of the diagonal blocks.
@@ -39,6 +41,31 @@ def nonneg_chunk(S: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write
                                  ops._stream()), "triad_nonneg_chunk")
 
 
+#: use the fused tcgen05 forward (triad_nonneg_fused_chunk) when the shape allows; False forces the library-GEMM +
+#: elementwise path (kept for fp32 inputs, odd shapes and as a cross-check)
+USE_FUSED = True
+
+
+def fused_supported(q: torch.Tensor, v: torch.Tensor) -> bool:
+    D, Nv = q.shape[-1], v.shape[1]
+    return q.dtype == torch.bfloat16 and D % 64 == 0 and D <= 512 and Nv <= 256 and Nv % 8 == 0
+
+
+def nonneg_fused_chunk(q: torch.Tensor, vc: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write_grad: bool,
+                       sums: torch.Tensor):
+    """N = dl_nonneg/d<q,v> for all rows of q against the images vc ([M, jc*Nv] bf16, or None when write_grad is
+    False), straight from the tensor-core forward; accumulates into sums (fp64 [2])."""
+    lib = _lib.load()
+    Bq, Nq, D = q.shape
+    jc, Nv, _ = vc.shape
+    N = torch.empty(Bq * Nq, jc * Nv, dtype=torch.bfloat16, device=q.device) if write_grad else None
+    ws = ops._Workspace.get(lib.triad_nonneg_fused_workspace_bytes(), q.device, "nonneg_fused")
+    check(lib.triad_nonneg_fused_chunk(q.data_ptr(), vc.data_ptr(), T.data_ptr(), Bq, jc, Nq, Nv, D, float(lo), float(coef),
+                                       None if N is None else N.data_ptr(), jc * Nv, 1 if write_grad else 0,
+                                       sums.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()), "triad_nonneg_fused_chunk")
+    return N
+
+
 class DenseNonNeg(torch.autograd.Function):
     """l_nonneg = mean(clamp(T*<q,v>, lo, 0)^2) over all token pairs, with dq, dv, dT.
 
@@ -62,10 +89,14 @@ class DenseNonNeg(torch.autograd.Function):
         jc = max(1, min(Bv, int(chunk_bytes) // max(1, M * Nv * q.element_size())))
         dq32 = torch.zeros(M, D, dtype=torch.float32, device=q.device) if need else None
         dv = torch.empty_like(v) if need else None
+        fused = USE_FUSED and fused_supported(q, v)
         for j0 in range(0, Bv, jc):
             vc = v[j0:j0 + jc].reshape(-1, D)
-            S = torch.mm(q2, vc.t())                        # raw <q,v>, rounded to the input dtype like the reference's matmul
-            nonneg_chunk(S, T, lo, 2.0 / numel, need, sums)  # in place: S -> N = dl_nonneg/d<q,v>
+            if fused:       # the tcgen05 forward writes N itself (no S chunk, no elementwise pass)
+                S = nonneg_fused_chunk(q, v[j0:j0 + jc], T, lo, 2.0 / numel, need, sums)
+            else:
+                S = torch.mm(q2, vc.t())                        # raw <q,v>, rounded to the input dtype like the reference's matmul
+                nonneg_chunk(S, T, lo, 2.0 / numel, need, sums)  # in place: S -> N = dl_nonneg/d<q,v>
             if need:
                 dq32.add_(torch.mm(S, vc))
                 dv[j0:j0 + jc] = torch.mm(S.t(), q2).view(-1, Nv, D)
