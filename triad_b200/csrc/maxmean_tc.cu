@@ -49,7 +49,7 @@ constexpr int kTmemCols = 512;
 constexpr uint32_t kQkbBytes = kBlockM * kBlockK * 2;        // 16 KB
 constexpr uint32_t kQBytes = kMaxKB * kQkbBytes;             // 128 KB
 constexpr uint32_t kVRingBytes = 96 * 1024;
-constexpr uint32_t kBarBytes = 512;
+constexpr uint32_t kBarBytes = 1024;          // mbarriers, the TMEM base, and the 512-byte argmax exchange of the epilogue pairs
 constexpr uint32_t kSmemBytes = kQBytes + kVRingBytes + kBarBytes + 1024;   // + alignment slack
 
 struct Params {
@@ -130,6 +130,7 @@ constexpr uint32_t kStgPitch = 48;                                  // bytes per
 constexpr uint32_t kStgBytesPerWarp = 32 * kStgPitch;               // 1536 (8 epilogue warps: 12 KB, inside one ring stage)
 constexpr int kEmitEpiWarps = 8;                                    // two per scheduler: columns [0,128) and [128,256)
 constexpr int kEmitThreads = (kEpiWarp0 + kEmitEpiWarps) * 32;      // 384
+constexpr uint16_t kNoCol = 0xffffu;                                // "no column of my half reaches the threshold"
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -249,7 +250,7 @@ struct TileIter {
 // kSub = false: one accumulator tile per image (Nv <= 256), the training shapes' hot path;
 // kSub = true : n_sub 256-patch sub-tiles per image.
 template <int kCtaGroup, bool kSub, bool kEmitN = false>
-__global__ void __launch_bounds__(kEmitN ? kEmitThreads : kThreads, 1)
+__global__ void __launch_bounds__(kEmitThreads, 1)
 maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
                   const Params p) {
     constexpr int kVStageBytes = (kMaxN / kCtaGroup) * kBlockK * 2;       // 32 KB / 16 KB
@@ -270,6 +271,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const uint32_t bar_t_full = bar_v_empty + 8 * kStages;      // [2]
     const uint32_t bar_t_empty = bar_t_full + 16;               // [2]
     const uint32_t tmem_ptr_smem = bar_t_empty + 16;            // u32
+    const uint32_t xch_smem = bar_base + 512;                   // u16 [2 parities][128 rows]: epilogue pair exchange
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
@@ -296,7 +298,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int i = 0; i < kMaxKB; ++i) mbar_init(bar_q_full + 8 * i, 1);
         mbar_init(bar_q_empty, 1);
         for (int i = 0; i < kStages; ++i) { mbar_init(bar_v_full + 8 * i, 1); mbar_init(bar_v_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_t_full + 8 * i, 1); mbar_init(bar_t_empty + 8 * i, (kEmitN ? kEmitEpiWarps : 4) * kCtaGroup); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_t_full + 8 * i, 1); mbar_init(bar_t_empty + 8 * i, ((kEmitN || p.idx != nullptr) ? kEmitEpiWarps : 4) * kCtaGroup); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<kCtaGroup>(tmem_ptr_smem, kTmemCols);
@@ -503,9 +505,16 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
             p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp >= kEpiWarp0 && (p.idx != nullptr || warp < kEpiWarp0 + 4)) {
         // =============================== epilogue =======================================
+        // Two warps per TMEM lane quarter (one per scheduler pair): both take the row maximum over all columns
+        // (cheap: FMNMX3), then each searches ITS half of the columns for the first one that reaches the
+        // threshold (the expensive pass); the upper half hands its result to the lower-half warp through 2 bytes
+        // of shared memory and a 64-thread named barrier, and the lower-half warp alone writes idx / partial sums.
+        // (One warp per scheduler has to issue ~1 600 dependent instructions per tile within the tile's MMA time.)
+        // Forward-only calls (no idx) have no second pass: the upper-half warps sit out.
         const int quarter = warp & 3;
+        const int half = (warp - kEpiWarp0) >> 2;
         const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
         float Tval = *p.T;
         if (p.inv_T) Tval = 1.0f / Tval;
@@ -563,17 +572,20 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             //      argmax).  Same pipelined loads, walking the chunks from the last to the first so the lowest
             //      qualifying column is the one that sticks; inside a chunk four independent 8-column
             //      compare/select chains instead of one 256-long dependent chain. ----
-            int best = 0;
+            int best = (int)kNoCol;
             if (p.idx != nullptr) {
+                constexpr int kHalfCh = kCh / 2;
+                const int cb = half * kHalfCh;                   // this warp's chunks: [cb, cb + kHalfCh)
                 uint32_t bufA[32], bufB[32];
-                tmem_ld32_raw(taddr + (kCh - 1) * 32, bufA);
+                tmem_ld32_raw(taddr + (cb + kHalfCh - 1) * 32, bufA);
                 tmem_wait_ld();
 #pragma unroll
-                for (int c = kCh - 1; c >= 0; c -= 2) {
+                for (int cc = kHalfCh - 1; cc >= 0; cc -= 2) {
+                    const int c = cb + cc;
                     tmem_ld32_raw(taddr + (c - 1) * 32, bufB);
                     first_ge32(bufA, c * 32, Nv, theta, best);
                     tmem_wait_ld();
-                    if (c - 2 >= 0) tmem_ld32_raw(taddr + (c - 2) * 32, bufA);           // compile-time condition
+                    if (cc - 2 >= 0) tmem_ld32_raw(taddr + (c - 2) * 32, bufA);          // compile-time condition
                     first_ge32(bufB, (c - 1) * 32, Nv, theta, best);
                     tmem_wait_ld();
                 }
@@ -585,11 +597,24 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if constexpr (kCtaGroup == 2) mbar_arrive_cluster(t_empty_sig + 8 * acc);
                 else mbar_arrive_local(bar_t_empty + 8 * acc);
             }
+            if (p.idx != nullptr) {
+                // pair exchange (double buffered by tile parity: the upper-half warp may already be one tile ahead)
+                const uint32_t slot = xch_smem + ((t_cnt & 1u) * 128u + (uint32_t)(quarter * 32 + lane)) * 2u;
+                if (half == 1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(slot), "h"((uint16_t)best) : "memory");
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                if (half == 0) {
+                    uint16_t other;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(other) : "r"(slot) : "memory");
+                    if (best == (int)kNoCol) best = (other == kNoCol) ? 0 : (int)other;
+                }
+            }
+            if (half == 1) continue;                             // the lower-half warp owns the outputs
             // Equal rounded maxima in two sub-tiles: the earlier one holds the first index (torch.max), and
             // inside a sub-tile `best` already is the first column of that rounded value.
             if (sb == 0 || R > R_run) { R_run = R; best_run = best + sb * kMaxN; }
           }
             if (!alive) break;
+            if (half == 1) continue;
             if (p.idx != nullptr && r_orig >= 0) {
                 if (p.idx16) reinterpret_cast<uint16_t*>(p.idx)[(size_t)t.j * idx_pitch + idx_off] = (uint16_t)best_run;
                 else p.idx[(size_t)t.j * idx_pitch + idx_off] = (uint8_t)best_run;
@@ -661,7 +686,7 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& 
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * kCtaGroup));
-    cfg.blockDim = dim3(kEmitN ? kEmitThreads : kThreads);
+    cfg.blockDim = dim3(kEmitThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
