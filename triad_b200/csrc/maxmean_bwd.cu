@@ -851,7 +851,7 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
                             dv_gather_grouped_kernel<OUT, U, W, MB><<<grid_, 256, 0, st>>>(qb16, entries, segc, Tp, J0, nj, n_groups, Nv, D, wps_, b > 0, DST); \
                         } while (0)
 #define TRIAD_DVG(OUT, DST, J0) \
-                        if (wide_rows) TRIAD_DVG_K(OUT, DST, J0, 4, 2, 3); else TRIAD_DVG_K(OUT, DST, J0, 8, 1, 3);
+                        if (wide_rows) TRIAD_DVG_K(OUT, DST, J0, 4, 2, 4); else TRIAD_DVG_K(OUT, DST, J0, 8, 1, 3);
                         if (pl.scratch) { TRIAD_DVG(float, scratch, 0) }
                         else if (out_f32) { TRIAD_DVG(float, (float*)dv, j0) }
                         else { TRIAD_DVG(__nv_bfloat16, (__nv_bfloat16*)dv, j0) }
@@ -880,7 +880,7 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
                             dv_gather_bf16_kernel<OUT, U, W, MB><<<grid_, 256, 0, st>>>(qb16, entries, seg, Tp, J0, nj, Nv, D, wps_, Mb, b > 0, DST); \
                         } while (0)
 #define TRIAD_DVG(OUT, DST, J0) \
-                        if (wide_rows) TRIAD_DVG_K(OUT, DST, J0, 4, 2, 3); else TRIAD_DVG_K(OUT, DST, J0, 8, 1, 3);
+                        if (wide_rows) TRIAD_DVG_K(OUT, DST, J0, 4, 2, 4); else TRIAD_DVG_K(OUT, DST, J0, 8, 1, 3);
                         if (pl.scratch) { TRIAD_DVG(float, scratch, 0) }
                         else if (out_f32) { TRIAD_DVG(float, (float*)dv, j0) }
                         else { TRIAD_DVG(__nv_bfloat16, (__nv_bfloat16*)dv, j0) }
