@@ -12,6 +12,13 @@
 // sort of the rows by winning patch (one byte keys) gives every (image, patch) its list of
 // (row, weight) pairs, and a warp then accumulates that list in registers — no atomics, fixed
 // summation order, bit-reproducible.
+//
+// dv code paths (all produce the same lists in the same order, hence bit-identical results; the tests compare them):
+//   bf16, Nv <= 1024 (the training shapes): dv_group_sort_kernel (shared-memory sort per image x 8192-row group)
+//                                            -> dv_gather_grouped_kernel (packed rows, FFMA2, 64 registers);
+//   bf16, Nv  > 1024:                        dv_count / dv_offsets / dv_scatter_sort (global sort) -> dv_gather_bf16_kernel;
+//   fp32 inputs or TRIAD_BWD_GENERIC_DV:     the global sort -> dv_gather_kernel (generic, the cross-check).
+// dq lives in bwd_dq_tile.cu (TMA / shared-memory tiles) with dq_gather_kernel here as the generic path.
 #include "common.cuh"
 
 namespace triad {
