@@ -170,6 +170,42 @@ def test_golden_total_loss_with_regularisers(case, chunk_bytes, fused, monkeypat
     assert abs(m.temperature.grad.item() - T64.grad.item()) <= rtol * abs(T64.grad.item()) + 1e-9
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_nonneg_pressure_reaches_the_clamp_floor(fused, monkeypatch):
+    """Similarities below the clamp floor (lo = -20): the value clamps there and the gradient is gated off
+    (torch.clamp's backward).  The fused tcgen05 path detects such tiles by their row minimum and redoes them
+    with the reference's rounding; the library-GEMM path applies the gate per element."""
+    from triad_b200 import regularizers as R
+    monkeypatch.setattr(R, "USE_FUSED", fused)
+    B, Nq, Nv, D, T, lo = 6, 40, 64, 64, 1.5, -20.0
+    g = torch.Generator().manual_seed(5)
+    q = (torch.randn(B, Nq, D, generator=g) * 1.2).bfloat16()
+    v = (torch.randn(B, Nv, D, generator=g) * 1.2).bfloat16()
+    q64, v64 = q.double().requires_grad_(), v.double().requires_grad_()
+    T64 = torch.tensor(T, dtype=torch.float64, requires_grad=True)
+    tok = torch.einsum("iad,jpd->ijap", q64, v64) * T64
+    assert (tok < lo).float().mean().item() > 0.01           # the floor is really reached
+    ref = tok.clamp(min=lo, max=0).pow(2).mean()
+    ref.backward()
+    qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    Td = torch.nn.Parameter(torch.tensor(T, device="cuda"))
+    val = R.nonneg_pressure(qd, vd, Td, lo)
+    val.backward()
+    assert abs(val.item() - ref.item()) <= 1e-2 * ref.item()
+    # Both paths round S to bf16 twice near the floor, exactly like the reference under autocast (model.py:387): at
+    # |S| ~ 20 a bf16 ulp is 0.125, similarities within an ulp of the floor fall on either side of the gradient
+    # gate, and they are the largest terms — the reference's own bf16 graph is ~9 % away from fp64 here.  So the
+    # gradients are checked against that graph (ATen, bf16, materialised; small shape), and only loosely against fp64.
+    qb, vb = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    Tb = torch.nn.Parameter(torch.tensor(T, device="cuda"))
+    tb = torch.matmul(qb.unsqueeze(1).expand(-1, B, -1, -1), vb.unsqueeze(0).expand(B, -1, -1, -1).transpose(2, 3)) * Tb
+    torch.mean(torch.clamp(tb, min=lo, max=0) ** 2).backward()
+    assert rel_err(qd.grad.double().cpu(), qb.grad.double().cpu()) < 1e-2
+    assert rel_err(vd.grad.double().cpu(), vb.grad.double().cpu()) < 1e-2
+    assert abs(Td.grad.item() - Tb.grad.item()) <= 2e-2 * abs(Tb.grad.item())
+    assert rel_err(qd.grad.double().cpu(), q64.grad) < 0.15 and rel_err(vd.grad.double().cpu(), v64.grad) < 0.15
+
+
 @pytest.mark.parametrize("flags", [0, FWD_1CTA, FWD_SYNC, FWD_SYNC | FWD_1CTA])
 def test_tensor_core_vs_oracle_mid_size(flags):
     """B=24 x 250 x 256 x 512: tcgen05 argmax vs the CPU oracle.  Different fp32 accumulation

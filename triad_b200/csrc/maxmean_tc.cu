@@ -407,8 +407,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // ============ epilogue, dense-regulariser mode: N = coef*T*min(S,0) for every pair =============
         // One pass over the accumulator: s = T*acc, n = min(s, 0); the tile's sum of n^2 feeds the value and,
         // because n*s == n^2, also dL/dT (sum dS*<q,v> = sum n^2 / T).  The clamp floor `lo` (-60 / -20) is far
-        // outside the data range; a tile that does reach it (row minimum < lo) is redone exactly before its
-        // accumulator is released.  Padded text tokens take part, as in the reference (model.py:525).
+        // outside the data range; a tile that does come near it (row minimum within two bf16 ulps of lo) is redone
+        // with the reference's bf16 rounding of S, clamp and gradient gate before its accumulator is released.  Padded text tokens take part, as in the reference (model.py:525).
         const int quarter = warp & 3;
         const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
         const float Tval = *p.T;
@@ -455,7 +455,9 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             const float a2s = (a2[0] + a2[1]) + (a2[2] + a2[3]);
             const float mns = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
-            if (!__any_sync(0xffffffffu, vrow && mns < p.lo)) {
+            // (margin of two bf16 ulps: the reference clamps the bf16-ROUNDED similarity, so a value a hair above
+            //  the floor in fp32 can sit on it after rounding)
+            if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
                 if (vrow) { s2 += (double)a2s; sT += (double)a2s / (double)Tval; }
             } else {
                 // ---- exact pass (some similarity of this warp's rows is below the clamp floor): redo the tile with
@@ -472,8 +474,10 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                         float o[2];
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const float raw = __uint_as_float(buf[e + h]);
-                            const float sv = (c * 32 + e + h < p.Nv) ? raw * Tval : 0.f;
+                            // near the floor the reference's own rounding decides the gate: token_sims is
+                            // bf16(bf16(<q,v>) * T) under autocast (model.py:387), clamp and its gradient act on that
+                            const float raw = __bfloat162float(__float2bfloat16_rn(__uint_as_float(buf[e + h])));
+                            const float sv = (c * 32 + e + h < p.Nv) ? __bfloat162float(__float2bfloat16_rn(raw * Tval)) : 0.f;
                             const float n = fminf(sv, 0.f);
                             const float nc = fmaxf(n, p.lo);
                             e2 = fmaf(nc, nc, e2);
