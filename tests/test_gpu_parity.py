@@ -434,6 +434,40 @@ def test_sharded_step_single_rank_cuda(masked):
     assert abs(out["dT"].item() - ref["dT"].item()) < 1e-4 * (ref["g"].abs() * ref["clip"].abs().double()).sum().item()
 
 
+def test_two_modalities_one_backward_and_no_grad_eval():
+    """train.py computes an audio-visual and a text-visual loss in the same iteration and back-propagates their
+    sum: the second forward must not disturb anything the first one's backward needs (shared workspaces); and the
+    whole loss (with regularisers) evaluates under torch.no_grad() without building gradients."""
+    B, Na, Nt, Nv, D = 6, 40, 16, 64, 128
+    a, v, _ = O.make_inputs(B, Na, Nv, D, torch.bfloat16, seed=61)
+    t, _, mask = O.make_inputs(B, Nt, Nv, D, torch.bfloat16, seed=62, masked=True, min_len=2)
+    m = _model(1.5, regularizers=True)
+
+    def run(which):
+        ad, td, vd = a.cuda().requires_grad_(), t.cuda().requires_grad_(), v.cuda().requires_grad_()
+        m.temperature.grad = None
+        total = 0
+        if "av" in which:
+            clip, tok = m.compute_all_similarities_av(ad, vd)
+            total = total + m.compute_contrastive_loss_av(clip, tok)[0]
+        if "tv" in which:
+            clip2, tok2 = m.compute_all_similarities_tv(td, vd, mask.cuda())
+            total = total + m.compute_contrastive_loss_tv(clip2, tok2)[0]
+        total.backward()
+        z = lambda x: torch.zeros(1) if x is None else x.float().cpu()
+        return total.item(), z(ad.grad), z(td.grad), z(vd.grad), m.temperature.grad.item()
+
+    both, av, tv = run(("av", "tv")), run(("av",)), run(("tv",))
+    assert abs(both[0] - (av[0] + tv[0])) < 1e-5 * abs(both[0])
+    assert torch.equal(both[1], av[1]) and torch.equal(both[2], tv[2])           # da, dt: untouched by the other loss
+    assert rel_err(both[3], av[3] + tv[3]) < 1e-2                                 # dv accumulates both (bf16 adds)
+    assert abs(both[4] - (av[4] + tv[4])) < 1e-4 * max(1.0, abs(both[4]))
+    with torch.no_grad():
+        clip, tok = m.compute_all_similarities_av(a.cuda(), v.cuda())
+        total = m.compute_contrastive_loss_av(clip, tok)[0]
+    assert not total.requires_grad and abs(total.item() - av[0]) < 1e-5 * abs(av[0])
+
+
 def test_retrieval_against_reference_goldens():
     from triad_b200 import retrieval as R
     gold = load_golden("retrieval")
