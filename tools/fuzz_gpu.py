@@ -49,10 +49,27 @@ def run_cases(n, seed, verbose=True):
         loss.backward()
         torch.cuda.synchronize()
         idx = tok.argmax().cpu()
-        n_bad = int((idx != ref["idx"]).sum())
+        bad = (idx != ref["idx"]).nonzero()
+        n_bad = len(bad)
+        # A winner may differ from the CPU oracle's only where two candidates are a rounding-boundary near-tie (the fp32
+        # accumulation order decides which side of a bf16 boundary a dot product falls on): the exact similarities of the
+        # two candidates must then be within one bf16 ulp of each other.
+        near = True
+        for i, j, a in bad.tolist():
+            sx = (q[i, a].double() @ v[j].double().t()) * T
+            x, y = sx[idx[i, j, a]].item(), sx[ref["idx"][i, j, a]].item()
+            near = near and abs(x - y) <= 2 ** -7 * max(abs(x), 1e-30)
+        # gradients: against the closed form evaluated with the winners the GPU chose (a flipped near-tie on a DIAGONAL
+        # pair moves that row's gradient by as much as the row itself: g[i,i] is ~B times any other weight)
+        if n_bad:
+            rdq, rdv, _ = O.maxmean_backward(q, v, idx, ref["g"], T, ref["row_scale"], ref["clip"])
+        else:
+            rdq, rdv = ref["dq"], ref["dv"]
         errs = {"clip": rel(tok.clip.detach().cpu(), ref["clip"]), "loss": abs(loss.item() - ref["loss"].item()) / max(abs(ref["loss"].item()), 1e-9),
-                "dq": rel(qd.grad.cpu(), ref["dq"]), "dv": rel(vd.grad.cpu(), ref["dv"])}
-        ok = n_bad <= max(2, 1e-3 * idx.numel()) and errs["clip"] < 1e-4 and errs["loss"] < 1e-4 and errs["dq"] < 6e-3 and errs["dv"] < 6e-3
+                "dq": rel(qd.grad.cpu(), rdq), "dv": rel(vd.grad.cpu(), rdv)}
+        # one row maximum landing on the other side of a bf16 boundary moves a clip element by 2^-8 / Nq
+        clip_tol = 1e-4 + 2e-3 / Nq
+        ok = near and n_bad <= max(2, 1e-3 * idx.numel()) and errs["clip"] < clip_tol and errs["loss"] < 1e-4 and errs["dq"] < 6e-3 and errs["dv"] < 6e-3
         if masked and bool((mask == 0).any()):
             ok = ok and qd.grad[mask.cuda() == 0].abs().max().item() == 0.0
         line = (f"{'ok  ' if ok else 'FAIL'} B={B} Nq={Nq} Nv={Nv} D={D} masked={masked} T={T} idx_mismatch={n_bad} "
