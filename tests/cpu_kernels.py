@@ -56,6 +56,19 @@ class OracleKernels:
         return dq.to(q.dtype), dv.float()
 
 
+def _nonneg_cpu(q, v, T, lo, numel):
+    """fp64 autograd of sum clamp(T<q,v>, lo, 0)^2 / numel (the dense term of model.py:411-412 / :525-526)."""
+    q64, v64 = q.double().requires_grad_(), v.double().requires_grad_()
+    T64 = torch.tensor(float(T), dtype=torch.float64, requires_grad=True)
+    tok = torch.einsum("iad,jpd->ijap", q64, v64) * T64
+    s2 = tok.clamp(min=lo, max=0).pow(2).sum()
+    (s2 / numel).backward()
+    return s2.detach(), q64.grad.to(q.dtype), v64.grad.float(), T64.grad
+
+
+OracleKernels.nonneg = lambda self, q, v, T, lo, numel: _nonneg_cpu(q, v, T, lo, numel)
+
+
 class PipelinedOracleKernels(OracleKernels):
     """Adds the split dv / dq entry points, so the sharded step takes its pipelined (per-destination reduce) path."""
 

@@ -73,3 +73,51 @@ def test_single_process_path():
     ref = O.contrastive_step_closed_form(q, v, 1.2)
     assert abs(out["loss"].item() - ref["loss"].item()) < 1e-5
     assert torch.allclose(out["dq"].double(), ref["dq"], atol=1e-7)
+
+
+def _reg_worker(rank, world, port, kind, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.cpu_kernels import OracleKernels
+        from triad_b200.dist import sharded_regularizer_step
+        B, Nq, Nv, D = 6, 9, 20, 16
+        q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.float32, seed=8)
+        q, v = q * 3, v * 3                                   # some similarities below zero by a margin
+        Bl = B // world
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        out = sharded_regularizer_step(q[sl], v[sl], torch.tensor(0.9), kind, kernels=OracleKernels(),
+                                       patch_sparsity_threshold=0.02, patch_sparsity_weight=0.5)
+        ret[rank] = {k: (val.item() if val.dim() == 0 else val) for k, val in out.items()}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["av", "tv"])
+def test_two_rank_regularisers_match_full_batch(kind):
+    """sharded_regularizer_step over 2 ranks == the oracle's restatement of model.py:394-428 / :516-542 on the
+    whole batch (value and the gradients w.r.t. every shard and the temperature), fp64 autograd."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_reg_worker, args=(world, _free_port(), kind, ret), nprocs=world, join=True)
+    B, Nq, Nv, D = 6, 9, 20, 16
+    q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.float32, seed=8)
+    q64, v64 = (q * 3).double().requires_grad_(), (v * 3).double().requires_grad_()
+    T64 = torch.tensor(0.9, dtype=torch.float64, requires_grad=True)     # T < 1: the calibration term is active
+    tok = torch.einsum("iad,jpd->ijap", q64, v64) * T64
+    if kind == "av":
+        reg, smooth = O.regularization_av(tok, T64)
+    else:
+        reg = O.regularization_tv(tok, 0.02, 0.5)
+    reg.backward()
+    Bl = B // world
+    for r in range(world):
+        o = ret[r]
+        assert abs(o["reg"] - reg.item()) < 1e-5 * abs(reg.item())
+        assert abs(o["dT"] - T64.grad.item()) < 1e-4 * abs(T64.grad.item())
+        assert torch.allclose(o["dq"].double(), q64.grad[r * Bl:(r + 1) * Bl], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(o["dv"].double(), v64.grad[r * Bl:(r + 1) * Bl], rtol=1e-4, atol=1e-7)
+        if kind == "av":
+            assert abs(o["smooth"] - smooth.item()) < 1e-5 * abs(smooth.item())

@@ -434,6 +434,27 @@ def test_sharded_step_single_rank_cuda(masked):
     assert abs(out["dT"].item() - ref["dT"].item()) < 1e-4 * (ref["g"].abs() * ref["clip"].abs().double()).sum().item()
 
 
+@pytest.mark.parametrize("kind", ["av", "tv"])
+def test_sharded_regulariser_step_single_rank_cuda(kind):
+    """triad_b200.dist.sharded_regularizer_step with the product kernels on one rank vs fp64 autograd of the oracle's
+    restatement (the 2-rank collectives are covered by the gloo tests)."""
+    from triad_b200.dist import sharded_regularizer_step
+    B, Nq, Nv, D, T = 8, 24, 64, 128, 0.9
+    q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=71)
+    q, v = (q.float() * 3).bfloat16(), (v.float() * 3).bfloat16()
+    q64, v64 = q.double().requires_grad_(), v.double().requires_grad_()
+    T64 = torch.tensor(T, dtype=torch.float64, requires_grad=True)
+    tok = torch.einsum("iad,jpd->ijap", q64, v64) * T64
+    reg = O.regularization_av(tok, T64)[0] if kind == "av" else O.regularization_tv(tok, 0.01, 0.5)
+    reg.backward()
+    out = sharded_regularizer_step(q.cuda(), v.cuda(), torch.tensor(T, device="cuda"), kind,
+                                   patch_sparsity_threshold=0.01, patch_sparsity_weight=0.5)
+    assert abs(out["reg"].item() - reg.item()) <= 1e-2 * abs(reg.item())
+    assert rel_err(out["dq"].double().cpu(), q64.grad) < 1e-2
+    assert rel_err(out["dv"].double().cpu(), v64.grad) < 1e-2
+    assert abs(out["dT"].item() - T64.grad.item()) <= 1e-2 * abs(T64.grad.item())
+
+
 def test_two_modalities_one_backward_and_no_grad_eval():
     """train.py computes an audio-visual and a text-visual loss in the same iteration and back-propagates their
     sum: the second forward must not disturb anything the first one's backward needs (shared workspaces); and the

@@ -10,7 +10,8 @@ queries and images [r*Bl,(r+1)*Bl).  One exchange each way:
             rank's images and with dQ  -> each rank receives the gradient of its own images
             (dQ is local; dT is a sum of the per-rank  sum g*clip  already in the 8 sums)
 
-There is no other data-path collective; per-rank work is (B/W) x B pairs.  Collectives go through
+There is no other data-path collective; per-rank work is (B/W) x B pairs.  sharded_regularizer_step() adds
+the reference's regularisation terms in the same sharding (one more reduce-scatter of a dv partial).  Collectives go through
 torch.distributed (NCCL over NVLink/NVSwitch on the GPU box; gloo in the CPU tests, where the
 four kernel entry points are injected by the test — the product binding below is CUDA-only).
 """
@@ -66,6 +67,14 @@ class CudaKernels:
         flags = _lib.BWD_PACK_ROWS if (self.packed and q.dtype == torch.bfloat16) else 0
         dq, _, _ = ops.maxmean_bwd(q, v, idx, g, None, scale, T, need_dq=True, need_dv=False, need_dT=False, flags=flags)
         return dq
+
+
+    def nonneg(self, q, v, T, lo, numel):
+        """Dense non-negative-pressure term of this rank's rows against ALL images, normalised by the global pair
+        count: (sum clamp^2 fp64 scalar, dq (Bq,Nq,D), dv partial (Bv,Nv,D) fp32, dT fp64 scalar)."""
+        from . import regularizers as R
+        sums, dq32, dv = R.nonneg_sweep(q, v, T, lo, numel, True, R.CHUNK_BYTES)
+        return sums[0], dq32.view(q.shape).to(q.dtype), dv.float(), sums[1]
 
 
 def _all_gather(x: torch.Tensor, W: int, group) -> torch.Tensor:
@@ -150,6 +159,69 @@ def sharded_contrastive_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
     out["dq"] = dq
     out["dv"] = dv32.to(v_local.dtype)
     out["dT"] = (all_sums[:, 6].sum() / T.double()).to(torch.float32)
+    return out
+
+
+def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, temperature: torch.Tensor, kind: str,
+                             group=None, kernels=None, patch_sparsity_threshold: float = 0.3,
+                             patch_sparsity_weight: float = 0.1) -> Dict[str, torch.Tensor]:
+    """The reference's regularisation terms (model.py:394-428 for kind "av", :516-542 for "tv") over a row-sharded
+    batch, with the gradients of the GLOBAL regulariser w.r.t. this rank's shards:
+
+      dense non-negative pressure   this rank's rows against all (all-gathered) images; value all-reduced, dq local,
+                                    the dv partial reduce-scattered like the contrastive one;
+      positive-pair terms           (temporal smoothness / patch sparsity on token_sims[i,i]) are local — a rank owns
+                                    both members of its positive pairs — and use the reference's ATen ops;
+      temperature calibration       a scalar on T ("av" only).
+
+    Returns {reg, smooth (0.01*l_smooth, "av"), dq (Bl,Nq,D), dv (Bl,Nv,D), dT}."""
+    from . import regularizers as R
+    if kind not in ("av", "tv"):
+        raise ValueError("kind must be 'av' or 'tv'")
+    k = kernels if kernels is not None else CudaKernels()
+    W = dist.get_world_size(group) if dist.is_initialized() else 1
+    r = dist.get_rank(group) if dist.is_initialized() else 0
+    Bl, Nq, D = q_local.shape
+    Nv = v_local.shape[1]
+    B = Bl * W
+    dev = q_local.device
+    q_local, v_local = q_local.detach().contiguous(), v_local.detach().contiguous()
+    T = temperature.detach().to(device=dev, dtype=torch.float32).reshape(())
+    v_all = _all_gather(v_local, W, group).view(B, Nv, D) if W > 1 else v_local
+
+    lo = -60.0 if kind == "av" else -20.0
+    numel = float(B) * B * Nq * Nv
+    s2, dq_nn, dv_nn_partial, dT_nn = k.nonneg(q_local, v_all, T, lo, numel)
+    dv_nn = _reduce_scatter_rows(dv_nn_partial, W, r, group) if W > 1 else dv_nn_partial
+
+    # positive pairs: the reference's own ops on this rank's diagonal blocks; the global mean is the mean of the
+    # per-rank means (equal shard sizes)
+    ql, vl = q_local.clone().requires_grad_(True), v_local.clone().requires_grad_(True)
+    Tl = T.clone().requires_grad_(True)
+    diag = R.positive_pair_token_sims(ql, vl, Tl)
+    if kind == "av":
+        term = R.temporal_smoothness(diag) if Nq > 1 else diag.sum() * 0
+        w_term = 0.01
+    else:
+        term = R.patch_sparsity(diag, patch_sparsity_threshold)
+        w_term = patch_sparsity_weight
+    (term.float() * (w_term / W)).backward()
+    scal = torch.stack([s2.double() / numel, term.detach().double() / W, dT_nn.double(), Tl.grad.double()])
+    if W > 1:
+        dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
+    l_nonneg, l_term, dT_nonneg, dT_term = scal[0], scal[1], scal[2], scal[3]
+    reg = 0.15 * l_nonneg + w_term * l_term
+    dT = 0.15 * dT_nonneg + dT_term
+    if kind == "av":                                   # 20 * relu(-log T)^2 (model.py:414-424)
+        Td = T.double()
+        neg_log = torch.clamp(-torch.log(Td), min=0)
+        reg = reg + 20.0 * neg_log ** 2
+        dT = dT - 40.0 * neg_log / Td
+    out = {"reg": reg.to(torch.float32), "dT": dT.to(torch.float32),
+           "dq": (0.15 * dq_nn.float() + ql.grad.float()).to(q_local.dtype),
+           "dv": (0.15 * dv_nn.float() + vl.grad.float()).to(v_local.dtype)}
+    if kind == "av":
+        out["smooth"] = (0.01 * l_term).to(torch.float32)
     return out
 
 

@@ -66,10 +66,39 @@ def nonneg_fused_chunk(q: torch.Tensor, vc: torch.Tensor, T: torch.Tensor, lo: f
     return N
 
 
+def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, numel: float, need_grads: bool,
+                 chunk_bytes: int):
+    """One sweep over image chunks.  Returns (sums fp64 [2] = {sum clamp^2, dl/dT for l = sum clamp^2 / numel},
+    dq fp32 [Bq*Nq, D] or None, dv [Bv,Nv,D] in the input dtype or None); the gradients are those of
+    sum clamp(T<q,v>, lo, 0)^2 / numel.  `numel` is the caller's normaliser (all pairs of the GLOBAL batch when the
+    rows are one rank's shard)."""
+    q, v = q.contiguous(), v.contiguous()
+    Bq, Nq, D = q.shape
+    Bv, Nv, _ = v.shape
+    M = Bq * Nq
+    q2 = q.view(M, D)
+    sums = torch.zeros(2, dtype=torch.float64, device=q.device)
+    jc = max(1, min(Bv, int(chunk_bytes) // max(1, M * Nv * q.element_size())))
+    dq32 = torch.zeros(M, D, dtype=torch.float32, device=q.device) if need_grads else None
+    dv = torch.empty_like(v) if need_grads else None
+    fused = USE_FUSED and fused_supported(q, v)
+    for j0 in range(0, Bv, jc):
+        vc = v[j0:j0 + jc].reshape(-1, D)
+        if fused:       # the tcgen05 forward writes N itself (no S chunk, no elementwise pass)
+            S = nonneg_fused_chunk(q, v[j0:j0 + jc], T, lo, 2.0 / numel, need_grads, sums)
+        else:
+            S = torch.mm(q2, vc.t())                        # raw <q,v>, rounded to the input dtype like the reference's matmul
+            nonneg_chunk(S, T, lo, 2.0 / numel, need_grads, sums)  # in place: S -> N = dl_nonneg/d<q,v>
+        if need_grads:
+            dq32.add_(torch.mm(S, vc))
+            dv[j0:j0 + jc] = torch.mm(S.t(), q2).view(-1, Nv, D)
+    return sums, dq32, dv
+
+
 class DenseNonNeg(torch.autograd.Function):
     """l_nonneg = mean(clamp(T*<q,v>, lo, 0)^2) over all token pairs, with dq, dv, dT.
 
-    The gradients are produced during the forward sweep (one S chunk GEMM serves both the value
+    The gradients are produced during the forward sweep (one pass over the similarities serves both the value
     and the gradient), saved, and scaled by the incoming gradient in backward."""
 
     @staticmethod
@@ -77,29 +106,12 @@ class DenseNonNeg(torch.autograd.Function):
         ops._require_cuda(q, v)
         if q.dtype != v.dtype or q.dtype not in (torch.float32, torch.bfloat16):
             raise TypeError("DenseNonNeg supports float32 and bfloat16 embeddings of one dtype")
-        q, v = q.contiguous(), v.contiguous()
         Bq, Nq, D = q.shape
         Bv, Nv, _ = v.shape
-        M = Bq * Nq
-        numel = float(M) * Bv * Nv
+        numel = float(Bq * Nq) * Bv * Nv
         T = ops.temperature_tensor(temperature, q.device)
         need = any(ctx.needs_input_grad[:3])
-        q2 = q.view(M, D)
-        sums = torch.zeros(2, dtype=torch.float64, device=q.device)
-        jc = max(1, min(Bv, int(chunk_bytes) // max(1, M * Nv * q.element_size())))
-        dq32 = torch.zeros(M, D, dtype=torch.float32, device=q.device) if need else None
-        dv = torch.empty_like(v) if need else None
-        fused = USE_FUSED and fused_supported(q, v)
-        for j0 in range(0, Bv, jc):
-            vc = v[j0:j0 + jc].reshape(-1, D)
-            if fused:       # the tcgen05 forward writes N itself (no S chunk, no elementwise pass)
-                S = nonneg_fused_chunk(q, v[j0:j0 + jc], T, lo, 2.0 / numel, need, sums)
-            else:
-                S = torch.mm(q2, vc.t())                        # raw <q,v>, rounded to the input dtype like the reference's matmul
-                nonneg_chunk(S, T, lo, 2.0 / numel, need, sums)  # in place: S -> N = dl_nonneg/d<q,v>
-            if need:
-                dq32.add_(torch.mm(S, vc))
-                dv[j0:j0 + jc] = torch.mm(S.t(), q2).view(-1, Nv, D)
+        sums, dq32, dv = nonneg_sweep(q, v, T, lo, numel, need, chunk_bytes)
         value = (sums[0] / numel).to(torch.float32)
         if need:
             ctx.save_for_backward(dq32.to(q.dtype).view(Bq, Nq, D), dv, sums[1].to(torch.float32))
