@@ -53,7 +53,7 @@ extern "C" {
 #define TRIAD_FWD_FORCE_SIMT   1   /* fp32-accumulate CUDA-core kernel (always used for fp32 inputs) */
 #define TRIAD_FWD_FORCE_1CTA   2   /* tcgen05 kernel with cta_group::1 (debug / small shapes)        */
 #define TRIAD_FWD_DIVIDE_BY_T  4   /* S = <q,v> / T (retrieval.py:108) instead of <q,v> * T          */
-#define TRIAD_FWD_SYNC_CHUNKS  8   /* test aid: chunk-synchronous tile order (the V > 96 MB path) with 3-image chunks */
+#define TRIAD_FWD_SYNC_CHUNKS  8   /* test aid: chunk-synchronous tile order (the V > 48 MB path) with 3-image chunks */
 #define TRIAD_FWD_PACK_ROWS   16   /* bf16 tensor-core path: rows whose row_scale is 0 (padded text tokens,
                                       model.py:509-512) are dropped before the GEMM; their idx entries read 0 */
 
@@ -117,6 +117,19 @@ int triad_infonce_finish(const float* clip_rows, int rows, int B, int row0,
                          float grad_scale, float* g, double* sums,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* Fused single-device head: the whole B x B matrix is on this GPU (row0 = 0, rows = B).  Two launches produce
+ * g and sums as triad_infonce_partial + triad_infonce_finish do (bit-identical), plus the scalars
+ *   out4[0] = contrastive loss = sums[0]/(2B)                       (model.py:453-459 / :572-578)
+ *   out4[1] = 20*relu(-log T)^2, the temperature-calibration term   (model.py:420-427); 0 when temperature == NULL
+ *   out4[2] = out4[0] + out4[1]
+ *   out4[3] = d out4[1] / dT
+ * so the loss needs no further arithmetic on the host side.  B <= 2048 (TRIAD_ERR_UNSUPPORTED beyond: use the
+ * partial/finish pair).  ws: triad_contrastive_head_workspace_bytes(B). */
+size_t triad_contrastive_head_workspace_bytes(int B);
+int triad_contrastive_head(const float* clip, int B, const float* temperature,
+                           float* g, double* sums, float* out4,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* ---- backward through max-mean ------------------------------------------------------- */
 /* Replaces autograd's backward of model.py:387-391:
  *   dq[i,a,:] = T*row_scale[r] * sum_j g[i,j] * v[j, idx[j][r], :]
@@ -133,6 +146,7 @@ int triad_infonce_finish(const float* clip_rows, int rows, int B, int row0,
 #define TRIAD_BWD_NO_PREFETCH  4   /* tiled dq without the prefetch.global.L1 look-ahead (A/B timing)      */
 #define TRIAD_BWD_PACK_ROWS   32   /* dq sweeps only the rows whose row_scale is non-zero (masked text tokens
                                       get an exact zero gradient without being gathered for)                */
+#define TRIAD_BWD_DQ_STAGED    64   /* dq: the round-1 kernel (winners/weights staged through shared memory) — cross-check */
 size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
 int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,
                       const float* clip, const float* row_scale, const float* temperature,

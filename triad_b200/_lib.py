@@ -16,6 +16,7 @@ OK = 0
 DTYPE_F32, DTYPE_BF16 = 0, 1
 FWD_DEFAULT, FWD_FORCE_SIMT, FWD_FORCE_1CTA, FWD_DIVIDE_BY_T, FWD_SYNC_CHUNKS, FWD_PACK_ROWS = 0, 1, 2, 4, 8, 16
 BWD_DEFAULT, BWD_GENERIC_DQ, BWD_GENERIC_DV, BWD_NO_PREFETCH, BWD_DQ_L1, BWD_SMALL_BLOCKS, BWD_PACK_ROWS = 0, 1, 2, 4, 8, 16, 32
+BWD_DQ_STAGED = 64
 
 # name -> (restype, argtypes); must list every symbol of include/triad_b200.h
 SIGNATURES = {
@@ -36,6 +37,9 @@ SIGNATURES = {
                                       c_void_p, c_size_t, c_void_p]),
     "triad_infonce_finish": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                      c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "triad_contrastive_head_workspace_bytes": (c_size_t, [c_int]),
+    "triad_contrastive_head": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
     "triad_maxmean_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "triad_maxmean_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_int, c_int, c_int, c_int,

@@ -391,11 +391,7 @@ bool dq_smem_supported(int Nv, int D, int dtype) { return dtype == TRIAD_DTYPE_B
 int launch_dq_smem(const void* v, const void* idx, const float* g, const float* row_scale, const float* Tp,
                    int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, const int* pack_maps, cudaStream_t st) {
     using namespace dq3;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TRIAD_CUDA_CHECK(cudaFuncSetAttribute(dq_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_set = true;
-    }
+    TRIAD_SET_MAX_SMEM(dq_smem_kernel, kSmemBytes);
     CUtensorMap mv;
     cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)Nv, (cuuint64_t)Bv};
     cuuint64_t strides[2] = {(cuuint64_t)D * 2, (cuuint64_t)Nv * D * 2};
@@ -417,11 +413,7 @@ static int launch_dq_t(const void* v, const void* idx, const float* g, const flo
                        int M, int Bv, int Nq, int Nv, int D, void* dq, cudaStream_t st) {
     using namespace dq2;
     auto kern = dq_tile_kernel<IdxT, kPF>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<IdxT>()));
-        attr_set = true;
-    }
+    TRIAD_SET_MAX_SMEM(kern, smem_bytes<IdxT>());
     const dim3 grid((unsigned)(D / kSlice), (unsigned)ceil_div(M, kRows));
     const int g_vec = (Bv % 4 == 0) && (((uintptr_t)g & 15) == 0);
     kern<<<grid, kThreads, smem_bytes<IdxT>(), st>>>((const __nv_bfloat16*)v, (const IdxT*)idx, g, row_scale, Tp, M, Bv, Nq, Nv, D,

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/triad_b200.h"
 #include "triad_round.h"
 
@@ -17,6 +19,20 @@ int fail_msg(int status, const char* msg);
     do {                                                                    \
         cudaError_t e__ = (expr);                                           \
         if (e__ != cudaSuccess) return ::triad::cuda_fail(e__, #expr);      \
+    } while (0)
+
+// Opt a kernel in to > 48 KB of dynamic shared memory.  The attribute is PER DEVICE, so the "already done" state is a
+// bit per device ordinal (one process may drive several GPUs, and autograd runs backward on its own threads).
+#define TRIAD_SET_MAX_SMEM(kern, bytes)                                                                       \
+    do {                                                                                                      \
+        static std::atomic<unsigned long long> done__{0ull};                                                  \
+        int dev__ = 0;                                                                                        \
+        TRIAD_CUDA_CHECK(cudaGetDevice(&dev__));                                                              \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                                \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                                              \
+            TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            done__.fetch_or(bit__, std::memory_order_release);                                                \
+        }                                                                                                     \
     } while (0)
 
 void count_launch();                                // triad_launch_count(): kernels launched by this library
@@ -77,6 +93,11 @@ bool tc_supported(int Nv, int D);
 bool dq_smem_supported(int Nv, int D, int dtype);
 int launch_dq_smem(const void* v, const void* idx, const float* g, const float* row_scale, const float* Tp,
                    int M, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag, const int* pack_maps, cudaStream_t st);
+// software-pipelined variant (bwd_dq_pipe.cu): rows addressed in the padded index space, register prefetch of winners
+bool dq_pipe_supported(int Nv, int D, int dtype);
+int launch_dq_pipe(const void* v, const void* idx, const float* g, const float* row_scale, const float* Tp,
+                   int Bq, int Bv, int Nq, int Nv, int D, void* dq, int* abort_flag,
+                   const int* glist, const int* n_groups_dev, int variant, cudaStream_t st);
 bool dq_tile_supported(int D, int dtype);
 int launch_dq_tile(const void* v, const void* idx, int idx_bytes, const float* g, const float* row_scale,
                    const float* Tp, int M, int Bv, int Nq, int Nv, int D, int prefetch, void* dq, cudaStream_t st);

@@ -37,7 +37,8 @@ static inline NceWs nce_ws_carve(void* ws, int rows, int B) {
 // ---- step 1a: one CTA = 32 rows; warps reduce rows, then threads own columns ---------------
 __global__ void __launch_bounds__(kNceThreads)
 nce_partial_kernel(const float* __restrict__ clip, int rows, int B,
-                   float* __restrict__ row_lse, float* __restrict__ chunk_part) {
+                   float* __restrict__ row_lse, float* __restrict__ chunk_part, unsigned int* __restrict__ ticket) {
+    if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;     // the fused head's "last block" ticket
     const int blk = blockIdx.x;
     const int r0 = blk * kNceRowsPerBlock;
     const int nr = min(kNceRowsPerBlock, rows - r0);
@@ -141,6 +142,112 @@ __global__ void nce_final_reduce_kernel(const double* __restrict__ blk_sums, int
     sums[k] = a;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused single-device head (the whole B x B matrix on this GPU): two launches instead of five
+// kernels plus the torch glue around them (loss division, temperature calibration, casts).
+//   launch 1: nce_partial_kernel (row LSE + per-block column partials); block 0 also zeroes the ticket.
+//   launch 2: nce_head_kernel — every CTA combines the column partials of ALL blocks itself (nblk <= 64:
+//             nblk*B floats out of L2), then gradient + statistics for its 32 rows; the last CTA to take a
+//             ticket reduces the per-block sums in block order (deterministic) and writes the scalars:
+//               out[0] = contrastive loss = sums[0] / (2B)                      (model.py:453-459)
+//               out[1] = 20 * relu(-log T)^2        (the l_cal term, model.py:420-427; 0 without T)
+//               out[2] = out[0] + out[1]
+//               out[3] = d out[1] / dT
+// ---------------------------------------------------------------------------------------------
+constexpr int kHeadMaxBlocks = 64;
+
+__global__ void __launch_bounds__(kNceThreads)
+nce_head_kernel(const float* __restrict__ clip, int B, const float* __restrict__ row_lse,
+                const float* __restrict__ chunk_part, int nblk, const float* __restrict__ Tptr,
+                float* __restrict__ g, double* __restrict__ blk_sums, unsigned int* __restrict__ ticket,
+                double* __restrict__ sums, float* __restrict__ out) {
+    extern __shared__ float col_lse_s[];                 // [B]
+    for (int c = threadIdx.x; c < B; c += kNceThreads) {
+        float m = -INFINITY;
+        for (int k = 0; k < nblk; ++k) m = fmaxf(m, chunk_part[((size_t)k * 2 + 0) * B + c]);
+        float s = 0.f;
+        for (int k = 0; k < nblk; ++k)
+            s += chunk_part[((size_t)k * 2 + 1) * B + c] * expf(chunk_part[((size_t)k * 2 + 0) * B + c] - m);
+        col_lse_s[c] = m + logf(s);
+    }
+    __syncthreads();
+
+    const int blk = blockIdx.x;
+    const int r0 = blk * kNceRowsPerBlock;
+    const int nr = min(kNceRowsPerBlock, B - r0);
+    const float inv2B = 0.5f / (float)B;
+    double loss = 0.0, sd = 0.0, sd2 = 0.0, so = 0.0, so2 = 0.0, gc = 0.0;
+    float mo = -INFINITY;
+    for (int rr = 0; rr < nr; ++rr) {
+        const int i = r0 + rr;
+        const float rl = row_lse[i];
+        const float* x = clip + (size_t)i * B;
+        float* gi = g + (size_t)i * B;
+        for (int c = threadIdx.x; c < B; c += kNceThreads) {
+            const float xc = x[c];
+            const float cl = col_lse_s[c];
+            float gv = expf(xc - rl) + expf(xc - cl);
+            if (c == i) {
+                gv -= 2.f;
+                loss += (double)(rl - xc) + (double)(cl - xc);
+                sd += xc; sd2 += (double)xc * xc;
+            } else {
+                so += xc; so2 += (double)xc * xc; mo = fmaxf(mo, xc);
+            }
+            gv *= inv2B;
+            gc += (double)gv * xc;
+            gi[c] = gv;
+        }
+    }
+    __shared__ double red[kNceThreads / 32][7];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    loss = warp_sum_d(loss); sd = warp_sum_d(sd); sd2 = warp_sum_d(sd2);
+    so = warp_sum_d(so); so2 = warp_sum_d(so2); gc = warp_sum_d(gc); mo = warp_max(mo);
+    if (lane == 0) {
+        red[warp][0] = loss; red[warp][1] = sd; red[warp][2] = sd2; red[warp][3] = so;
+        red[warp][4] = so2; red[warp][5] = (double)mo; red[warp][6] = gc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int k = threadIdx.x;
+        double a = red[0][k];
+        for (int w = 1; w < kNceThreads / 32; ++w) a = (k == 5) ? fmax(a, red[w][k]) : a + red[w][k];
+        blk_sums[(size_t)blk * 8 + k] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                  // this block's sums are visible before its ticket
+        is_last = atomicAdd(ticket, 1u) == (unsigned)gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        double a = 0.0;
+        if (k < 7) {
+            a = ((volatile double*)blk_sums)[k];
+            for (int b = 1; b < (int)gridDim.x; ++b) {
+                const double t = ((volatile double*)blk_sums)[(size_t)b * 8 + k];
+                a = (k == 5) ? fmax(a, t) : a + t;
+            }
+        }
+        sums[k] = a;
+        if (k == 0) {
+            const float con = (float)(a / (2.0 * (double)B));
+            float cal = 0.f, dcal = 0.f;
+            if (Tptr) {
+                const float T = *Tptr;
+                const float nl = -logf(T);
+                if (nl > 0.f) { cal = 20.f * nl * nl; dcal = -40.f * nl / T; }
+            }
+            out[0] = con; out[1] = cal; out[2] = con + cal; out[3] = dcal;
+        }
+    }
+}
+
 }  // namespace triad
 
 using namespace triad;
@@ -159,7 +266,7 @@ extern "C" int triad_infonce_partial(const float* clip_rows, int rows, int B, in
     cudaStream_t st = (cudaStream_t)stream;
     NceWs w = nce_ws_carve(ws, rows, B);
     const int nblk = nce_blocks(rows);
-    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip_rows, rows, B, row_lse, w.chunk_part);
+    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip_rows, rows, B, row_lse, w.chunk_part, nullptr);
     TRIAD_LAUNCH_CHECK("nce_partial_kernel");
     nce_combine_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.chunk_part, nblk, B, 0, col_part);
     TRIAD_LAUNCH_CHECK("nce_combine_kernel");
@@ -183,5 +290,33 @@ extern "C" int triad_infonce_finish(const float* clip_rows, int rows, int B, int
     TRIAD_LAUNCH_CHECK("nce_finish_kernel");
     nce_final_reduce_kernel<<<1, 32, 0, st>>>(w.blk_sums, nblk, sums);
     TRIAD_LAUNCH_CHECK("nce_final_reduce_kernel");
+    return TRIAD_OK;
+}
+
+// Workspace of the fused head: the partial/finish layout, then the ticket.
+extern "C" size_t triad_contrastive_head_workspace_bytes(int B) {
+    if (B <= 0) return 0;
+    return nce_ws_bytes(B, B) + 256;
+}
+
+extern "C" int triad_contrastive_head(const float* clip, int B, const float* temperature,
+                                      float* g, double* sums, float* out4,
+                                      void* ws, size_t ws_bytes, void* stream) {
+    if (!clip || !g || !sums || !out4 || !ws) return fail_msg(TRIAD_ERR_BAD_ARG, "contrastive_head: null pointer");
+    if (B <= 0) return fail_msg(TRIAD_ERR_BAD_SHAPE, "contrastive_head: bad B");
+    if (ws_bytes < triad_contrastive_head_workspace_bytes(B)) return fail_msg(TRIAD_ERR_WORKSPACE, "contrastive_head: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    NceWs w = nce_ws_carve(ws, B, B);
+    const int nblk = nce_blocks(B);
+    unsigned int* ticket = (unsigned int*)((char*)ws + nce_ws_bytes(B, B));
+    float* row_lse = w.col_lse;          // the [B] slot is free here: the head keeps the column LSE in shared memory
+    if (nblk > kHeadMaxBlocks || (size_t)B * 4 > 96 * 1024) {
+        return fail_msg(TRIAD_ERR_UNSUPPORTED, "contrastive_head: B too large for the fused head (use infonce_partial/finish)");
+    }
+    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip, B, B, row_lse, w.chunk_part, ticket);
+    TRIAD_LAUNCH_CHECK("nce_partial_kernel");
+    nce_head_kernel<<<nblk, kNceThreads, (size_t)B * 4, st>>>(clip, B, row_lse, w.chunk_part, nblk, temperature, g,
+                                                              w.blk_sums, ticket, sums, out4);
+    TRIAD_LAUNCH_CHECK("nce_head_kernel");
     return TRIAD_OK;
 }

@@ -20,6 +20,7 @@
 //   fp32 inputs or TRIAD_BWD_GENERIC_DV:     the global sort -> dv_gather_kernel (generic, the cross-check).
 // dq lives in bwd_dq_tile.cu (TMA / shared-memory tiles) with dq_gather_kernel here as the generic path.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace triad {
 
@@ -769,6 +770,13 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool
     return pl;
 }
 
+// experiment knob: TRIAD_DQ_VARIANT selects the ring depth / address form of dq_pipe_kernel (0 = shipped default)
+static int dq_pipe_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TRIAD_DQ_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 template <typename T, typename IdxT>
 static int bwd_typed(const void* q, const void* v, const void* idx, const float* g,
                      const float* clip, const float* row_scale, const float* Tp,
@@ -779,7 +787,12 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
     constexpr int E = Vec16<T>::kElems;
     const int kch = ceil_div(D / E, 32);
     if (dq && (kch < 1 || kch > 4)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
-    if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_smem_supported(Nv, D, TRIAD_DTYPE_BF16) &&
+    if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_pipe_supported(Nv, D, TRIAD_DTYPE_BF16) &&
+        !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1 | TRIAD_BWD_DQ_STAGED | TRIAD_BWD_PACK_ROWS))) {
+        // the software-pipelined shared-memory gather (bwd_dq_pipe.cu)
+        const int rc = launch_dq_pipe(v, idx, g, row_scale, Tp, Bq, Bv, Nq, Nv, D, dq, (int*)ws, nullptr, nullptr, dq_pipe_variant(), st);
+        if (rc) return rc;
+    } else if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_smem_supported(Nv, D, TRIAD_DTYPE_BF16) &&
         !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1))) {
         // TRIAD_BWD_PACK_ROWS (masked text queries): only the rows with a non-zero weight are swept
         const int* pack_maps = nullptr;
@@ -841,12 +854,7 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
                         const int n_groups = ceil_div((int)Mb, kGroupRows);
                         uint32_t* segc = (uint32_t*)((char*)ws + pl.off_segc);
                         auto skern = dv_group_sort_kernel<IdxT>;
-                        static bool attr_set = false;
-                        if (!attr_set) {
-                            TRIAD_CUDA_CHECK(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                                  (int)group_sort_smem(kGroupMaxNv)));
-                            attr_set = true;
-                        }
+                        TRIAD_SET_MAX_SMEM(skern, group_sort_smem(kGroupMaxNv));
                         skern<<<nj * n_groups, kGroupWarps * 32, group_sort_smem(Nv), st>>>(
                             idx_b, g_b, rs_b, img_pitch, j0, n_groups, (int)Mb, Bv, Nq, Nv, nq_pad, segc, entries);
                         TRIAD_LAUNCH_CHECK("dv_group_sort_kernel");

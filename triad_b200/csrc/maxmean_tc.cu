@@ -683,11 +683,7 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
 template <int kCtaGroup, bool kSub, bool kEmitN = false>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& p, int n_clusters, cudaStream_t st) {
     auto kern = maxmean_tc_kernel<kCtaGroup, kSub, kEmitN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TRIAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_set = true;
-    }
+    TRIAD_SET_MAX_SMEM(kern, kSmemBytes);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * kCtaGroup));
     cfg.blockDim = dim3(kEmitThreads);

@@ -21,6 +21,7 @@ never needed token_sims — is computed from ``clip_sims``.
 """
 from __future__ import annotations
 
+from collections.abc import Mapping
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -38,6 +39,7 @@ class TokenSims:
         self.clip = clip_f32            # fp32 (Bq,Bv), attached to the autograd graph
         self.idx_t = idx                # [Bv, Bq*nq_pad] uint8/uint16 (library layout)
         self.prefix = prefix
+        self.clip_out = clip_f32        # what compute_all_similarities_* returned as clip_sims (set by the caller)
         self.packed = False
         self.fwd_flags = 0
         self.shape = torch.Size((q.shape[0], v.shape[0], q.shape[1], v.shape[1]))
@@ -69,56 +71,55 @@ class TokenSims:
         return f"TokenSims(shape={tuple(self.shape)}, dtype={self.dtype}, device={self.device}, fused)"
 
 
-class LazyStats(dict):
+class LazyStats(Mapping):
     """The statistics dictionary of model.py:463-470, filled on first access.
 
     The reference pays five ``.item()`` device->host syncs per loss call to build this dict even
     when nobody looks at it.  Here the six values live in one small device tensor until a key is
     actually read (wandb logging, prints); the training step itself stays asynchronous, so the
-    backward kernels can be queued while the forward is still running."""
+    backward kernels can be queued while the forward is still running.
+
+    A read-only ``Mapping`` (not a ``dict`` subclass: C fast paths such as ``json.dumps`` or ``pickle`` read a
+    dict's storage directly and would see it empty).  ``wandb_dict.update(stats)``, ``stats[key]``,
+    ``key in stats``, ``stats.keys()``, ``dict(stats)`` and ``**stats`` work as with the reference's dict;
+    ``to_dict()`` / pickling / deepcopy give a plain dict."""
+
+    __slots__ = ("_pending", "_values")
 
     def __init__(self, sums: torch.Tensor, B: int, prefix: str):
-        super().__init__()
         self._pending = (sums, B, prefix)
+        self._values = None
 
-    def _fill(self):
-        if self._pending is not None:
+    def _fill(self) -> Dict[str, float]:
+        if self._values is None:
             sums, B, prefix = self._pending
+            self._values = _stats_from_sums(sums, B, prefix)
             self._pending = None
-            super().update(_stats_from_sums(sums, B, prefix))
+        return self._values
 
     def __getitem__(self, k):
-        self._fill(); return super().__getitem__(k)
+        return self._fill()[k]
 
     def __iter__(self):
-        self._fill(); return super().__iter__()
+        return iter(self._fill())
 
     def __len__(self):
-        self._fill(); return super().__len__()
-
-    def __contains__(self, k):
-        self._fill(); return super().__contains__(k)
-
-    def keys(self):
-        self._fill(); return super().keys()
-
-    def values(self):
-        self._fill(); return super().values()
-
-    def items(self):
-        self._fill(); return super().items()
-
-    def get(self, k, default=None):
-        self._fill(); return super().get(k, default)
+        return len(self._fill())
 
     def __repr__(self):
-        self._fill(); return super().__repr__()
+        return repr(self._fill())
 
-    def __eq__(self, other):
-        self._fill(); return super().__eq__(other)
+    def to_dict(self) -> Dict[str, float]:
+        return dict(self._fill())
 
-    def copy(self):
-        self._fill(); return dict(self)
+    def copy(self) -> Dict[str, float]:
+        return self.to_dict()
+
+    def __reduce__(self):
+        return (dict, (self.to_dict(),))
+
+    def __deepcopy__(self, memo):
+        return self.to_dict()
 
 
 def _stats_from_sums(sums: torch.Tensor, B: int, prefix: str) -> Dict[str, float]:
@@ -173,6 +174,7 @@ class TriadSimilarityMixin:
         # The reference's clip_sims dtype: bf16 for AV under autocast (mean of bf16 maxima,
         # model.py:391), fp32 for TV (mask.float() promotes, model.py:509-512) and for fp32 inputs.
         out = clip.to(q_feats.dtype) if attention_mask is None else clip
+        handle.clip_out = out
         return out, handle
 
     def compute_all_similarities_av(self, audio_feats, visual_feats):
@@ -184,10 +186,31 @@ class TriadSimilarityMixin:
         return self._similarities(text_feats, visual_feats, attention_mask, "tv")
 
     # -- losses -----------------------------------------------------------------------------
-    def _contrastive(self, clip_sims, token_sims, prefix) -> Tuple[torch.Tensor, Dict[str, float]]:
-        clip = token_sims.clip if isinstance(token_sims, TokenSims) else clip_sims
-        loss, sums = ops.SymmetricInfoNCE.apply(clip)
-        return loss, LazyStats(sums, clip.shape[0], prefix)
+    def _loss_head(self, clip_sims, token_sims, prefix, with_calibration):
+        """(contrastive, l_cal or None, contrastive + l_cal or None, stats).
+
+        The loss is computed from the ``clip_sims`` argument, as in the reference.  When that argument is the very
+        tensor compute_all_similarities_* returned next to the handle, the handle's fp32 copy of the same matrix
+        is used instead of its bf16 rounding (the reference's log_softmax runs in fp32 under autocast; the
+        unrounded input is the more accurate of the two and keeps one autograd path).  Anything else — a scaled,
+        detached or otherwise edited matrix — is honoured as given."""
+        clip = clip_sims
+        if isinstance(token_sims, TokenSims) and (clip_sims is token_sims.clip_out or clip_sims is token_sims.clip):
+            clip = token_sims.clip
+        if not isinstance(clip, torch.Tensor) or clip.dim() != 2:
+            raise ValueError("clip_sims must be the (B,B) clip-similarity matrix")
+        ops._require_cuda(clip)
+        B = clip.shape[0]
+        T = self.temperature if with_calibration else None
+        if B <= ops.HEAD_MAX_B:
+            con, cal, tot, sums = ops.ContrastiveHead.apply(clip, T)
+            if not with_calibration:
+                cal = tot = None
+        else:                                   # very large single-device batches: the block-wise kernels
+            con, sums = ops.SymmetricInfoNCE.apply(clip)
+            cal = self._temperature_calibration() if with_calibration else None
+            tot = con + cal if with_calibration else None
+        return con, cal, tot, LazyStats(sums, B, prefix)
 
     def _temperature_calibration(self) -> torch.Tensor:
         """20 * relu(-log T)^2 — the l_cal term of model.py:420-427 (a scalar on the parameter)."""
@@ -198,12 +221,18 @@ class TriadSimilarityMixin:
 
     def compute_regularization_losses_av(self, token_sims):
         """(reg, 0.01*l_smooth) — model.py:410-428: 20*l_cal + 0.15*mean(clamp(S,-60,0)^2) + 0.01*l_smooth."""
+        return self._regularization_av(token_sims, None)
+
+    def _regularization_av(self, token_sims, l_cal):
+        """compute_regularization_losses_av with the calibration term already evaluated by the fused head."""
         from . import regularizers as R
         tok = token_sims
         l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -60.0)
         diag = R.positive_pair_token_sims(tok.q, tok.v, self.temperature)
         l_smooth = R.temporal_smoothness(diag)
-        reg = self._temperature_calibration() + 0.15 * l_nonneg + 0.01 * l_smooth
+        if l_cal is None:
+            l_cal = self._temperature_calibration()
+        reg = l_cal + 0.15 * l_nonneg + 0.01 * l_smooth
         return reg, 0.01 * l_smooth
 
     def compute_regularization_losses_tv(self, token_sims):
@@ -223,17 +252,16 @@ class TriadSimilarityMixin:
         False`` (or a dense tensor in place of the handle) only the contrastive loss and the scalar
         temperature-calibration term are computed — the fused max-mean + InfoNCE path on its own, which
         is what BASELINE.json's metric times."""
-        contrastive, stats = self._contrastive(clip_sims, token_sims, "av")
+        contrastive, l_cal, con_plus_cal, stats = self._loss_head(clip_sims, token_sims, "av", True)
         if self._dense_terms_enabled(token_sims):
-            reg, smooth = self.compute_regularization_losses_av(token_sims)
-        else:
-            reg = self._temperature_calibration()
-            smooth = torch.zeros((), dtype=torch.float32, device=contrastive.device)
-        return contrastive + reg, contrastive, reg, smooth, stats
+            reg, smooth = self._regularization_av(token_sims, l_cal)
+            return contrastive + reg, contrastive, reg, smooth, stats
+        smooth = torch.zeros((), dtype=torch.float32, device=contrastive.device)
+        return con_plus_cal, contrastive, l_cal, smooth, stats
 
     def compute_contrastive_loss_tv(self, clip_sims, token_sims):
         """(total, stats) — model.py:544-593 (see compute_contrastive_loss_av for the regulariser switch)."""
-        contrastive, stats = self._contrastive(clip_sims, token_sims, "tv")
+        contrastive, _, _, stats = self._loss_head(clip_sims, token_sims, "tv", False)
         if self._dense_terms_enabled(token_sims):
             return contrastive + self.compute_regularization_losses_tv(token_sims), stats
         return contrastive, stats
@@ -250,9 +278,10 @@ class TriadSimilarityMixin:
         N2 = f2.shape[1]
         T = ops.temperature_tensor(self.temperature, f1.device)
         out = torch.empty(B, N1, N2, dtype=torch.float32, device=f1.device)
-        _lib.check(lib.triad_similarity_matrix(f1.data_ptr(), f2.data_ptr(), T.data_ptr(), B, N1, N2, D,
-                                               out.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                   "triad_similarity_matrix")
+        with ops._on(f1):
+            _lib.check(lib.triad_similarity_matrix(f1.data_ptr(), f2.data_ptr(), T.data_ptr(), B, N1, N2, D,
+                                                   out.data_ptr(), ops._stream(f1.device)),
+                       "triad_similarity_matrix")
         return out
 
 

@@ -20,8 +20,15 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    """Raw handle of torch's current stream ON `device` (the tensors' device, not the process-wide current one)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Device guard for one library call: the kernels are launched on the device that owns `t`, whatever the
+    process-wide current device is (several GPUs in one process, autograd's backward threads)."""
+    return torch.cuda.device(t.device)
 
 
 def _require_cuda(*ts: torch.Tensor) -> None:
@@ -36,7 +43,7 @@ class _Workspace:
 
     @classmethod
     def get(cls, nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
-        key = (device.index, _stream(), tag)
+        key = (device.index, _stream(device), tag)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1024), dtype=torch.uint8, device=device)
@@ -64,15 +71,32 @@ def temperature_tensor(temperature, device) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # raw calls
 # ----------------------------------------------------------------------------------------------
+_uniform_scale: Dict[Tuple, torch.Tensor] = {}
+
+
 def row_scale(mask: Optional[torch.Tensor], Bq: int, Nq: int, device) -> torch.Tensor:
     lib = _lib.load()
+    device = torch.device(device)
+    if mask is None:
+        # 1/Nq for every row (model.py:391): a constant of the shape — computed once, not once per step
+        key = (device.index, Bq, Nq)
+        out = _uniform_scale.get(key)
+        if out is None:
+            out = torch.empty(Bq * Nq, dtype=torch.float32, device=device)
+            with torch.cuda.device(device):
+                check(lib.triad_row_scale(None, Bq, Nq, out.data_ptr(), _stream(device)), "triad_row_scale")
+                torch.cuda.current_stream(device).synchronize()      # read-only from here on, from any stream
+            if len(_uniform_scale) > 64:
+                _uniform_scale.clear()
+            _uniform_scale[key] = out
+        return out
+    _require_cuda(mask)
     out = torch.empty(Bq * Nq, dtype=torch.float32, device=device)
-    if mask is not None:
-        _require_cuda(mask)
-        mask = mask.to(torch.int64).contiguous()
-        if mask.shape != (Bq, Nq):
-            raise ValueError(f"attention_mask must be ({Bq},{Nq}), got {tuple(mask.shape)}")
-    check(lib.triad_row_scale(_ptr(mask), Bq, Nq, out.data_ptr(), _stream()), "triad_row_scale")
+    mask = mask.to(torch.int64).contiguous()
+    if mask.shape != (Bq, Nq):
+        raise ValueError(f"attention_mask must be ({Bq},{Nq}), got {tuple(mask.shape)}")
+    with torch.cuda.device(device):
+        check(lib.triad_row_scale(_ptr(mask), Bq, Nq, out.data_ptr(), _stream(device)), "triad_row_scale")
     return out
 
 
@@ -107,12 +131,14 @@ def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.
     clip = torch.empty(Bq, Bv, dtype=torch.float32, device=q.device)
     idx = torch.empty(Bv, Bq * nq_padded(Nq), dtype=idx_dtype(Nv), device=q.device) if want_idx else None
     nws = lib.triad_maxmean_fwd_workspace_bytes_ex(Bq, Bv, Nq, Nv, D, dt, int(flags))
-    ws = _Workspace.get(nws, q.device, "fwd")
-    check(lib.triad_maxmean_fwd(q.data_ptr(), v.data_ptr(), scale.data_ptr(), T.data_ptr(),
-                                Bq, Bv, Nq, Nv, D, dt, clip.data_ptr(), _ptr(idx),
-                                ws.data_ptr(), ws.numel(), flags, _stream()), "triad_maxmean_fwd")
-    if check_watchdog:
-        check(lib.triad_maxmean_fwd_status(ws.data_ptr(), _stream()), "triad_maxmean_fwd (watchdog)")
+    with _on(q):
+        ws = _Workspace.get(nws, q.device, "fwd")
+        st = _stream(q.device)
+        check(lib.triad_maxmean_fwd(q.data_ptr(), v.data_ptr(), scale.data_ptr(), T.data_ptr(),
+                                    Bq, Bv, Nq, Nv, D, dt, clip.data_ptr(), _ptr(idx),
+                                    ws.data_ptr(), ws.numel(), flags, st), "triad_maxmean_fwd")
+        if check_watchdog:
+            check(lib.triad_maxmean_fwd_status(ws.data_ptr(), st), "triad_maxmean_fwd (watchdog)")
     return clip, idx
 
 
@@ -130,11 +156,12 @@ def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_d
           if need_dv else None)
     dT = torch.empty((), dtype=torch.float32, device=q.device) if need_dT else None
     nws = lib.triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dt)
-    ws = _Workspace.get(nws, q.device, "bwd")
-    check(lib.triad_maxmean_bwd(q.data_ptr(), v.data_ptr(), idx.data_ptr(), g.data_ptr(), _ptr(clip),
-                                scale.data_ptr(), T.data_ptr(), Bq, Bv, Nq, Nv, D, dt,
-                                _ptr(dq), _ptr(dv), 1 if dv_f32 else 0, _ptr(dT),
-                                ws.data_ptr(), ws.numel(), int(flags), _stream()), "triad_maxmean_bwd")
+    with _on(q):
+        ws = _Workspace.get(nws, q.device, "bwd")
+        check(lib.triad_maxmean_bwd(q.data_ptr(), v.data_ptr(), idx.data_ptr(), g.data_ptr(), _ptr(clip),
+                                    scale.data_ptr(), T.data_ptr(), Bq, Bv, Nq, Nv, D, dt,
+                                    _ptr(dq), _ptr(dv), 1 if dv_f32 else 0, _ptr(dT),
+                                    ws.data_ptr(), ws.numel(), int(flags), _stream(q.device)), "triad_maxmean_bwd")
     return dq, dv, dT
 
 
@@ -144,9 +171,10 @@ def infonce_partial(clip_rows: torch.Tensor, B: int, row0: int):
     row_lse = torch.empty(rows, dtype=torch.float32, device=clip_rows.device)
     col_part = torch.empty(2, B, dtype=torch.float32, device=clip_rows.device)
     nws = lib.triad_infonce_workspace_bytes(rows, B)
-    ws = _Workspace.get(nws, clip_rows.device, "nce")
-    check(lib.triad_infonce_partial(clip_rows.data_ptr(), rows, B, row0, row_lse.data_ptr(), col_part.data_ptr(),
-                                    ws.data_ptr(), ws.numel(), _stream()), "triad_infonce_partial")
+    with _on(clip_rows):
+        ws = _Workspace.get(nws, clip_rows.device, "nce")
+        check(lib.triad_infonce_partial(clip_rows.data_ptr(), rows, B, row0, row_lse.data_ptr(), col_part.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream(clip_rows.device)), "triad_infonce_partial")
     return row_lse, col_part
 
 
@@ -158,11 +186,30 @@ def infonce_finish(clip_rows, B, row0, row_lse, col_parts, grad_scale: float = 1
     g = torch.empty(rows, B, dtype=torch.float32, device=clip_rows.device)
     sums = torch.empty(8, dtype=torch.float64, device=clip_rows.device)
     nws = lib.triad_infonce_workspace_bytes(rows, B)
-    ws = _Workspace.get(nws, clip_rows.device, "nce")
-    check(lib.triad_infonce_finish(clip_rows.data_ptr(), rows, B, row0, row_lse.data_ptr(), col_parts.data_ptr(),
-                                   nparts, grad_scale, g.data_ptr(), sums.data_ptr(),
-                                   ws.data_ptr(), ws.numel(), _stream()), "triad_infonce_finish")
+    with _on(clip_rows):
+        ws = _Workspace.get(nws, clip_rows.device, "nce")
+        check(lib.triad_infonce_finish(clip_rows.data_ptr(), rows, B, row0, row_lse.data_ptr(), col_parts.data_ptr(),
+                                       nparts, grad_scale, g.data_ptr(), sums.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), _stream(clip_rows.device)), "triad_infonce_finish")
     return g, sums
+
+
+HEAD_MAX_B = 2048      # triad_contrastive_head: 64 row blocks of 32
+
+
+def contrastive_head(clip: torch.Tensor, T: Optional[torch.Tensor]):
+    """Fused single-device head: g fp32 [B,B], sums fp64 [8], out fp32 [4] = (contrastive, l_cal, sum, d l_cal/dT)."""
+    lib = _lib.load()
+    B = clip.shape[0]
+    g = torch.empty(B, B, dtype=torch.float32, device=clip.device)
+    sums = torch.empty(8, dtype=torch.float64, device=clip.device)
+    out = torch.empty(4, dtype=torch.float32, device=clip.device)
+    nws = lib.triad_contrastive_head_workspace_bytes(B)
+    with _on(clip):
+        ws = _Workspace.get(nws, clip.device, "head")
+        check(lib.triad_contrastive_head(clip.data_ptr(), B, _ptr(T), g.data_ptr(), sums.data_ptr(), out.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _stream(clip.device)), "triad_contrastive_head")
+    return g, sums, out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -176,6 +223,7 @@ class MaxMeanSimilarity(torch.autograd.Function):
     def forward(ctx, q, v, temperature, scale, flags):
         T = temperature_tensor(temperature, q.device)
         clip, idx = maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(q, v, T, scale, idx, clip)
         # rows dropped in the forward (zero weight) have no winners recorded: the backward must skip them too
         ctx.bwd_flags = _lib.BWD_PACK_ROWS if (flags & _lib.FWD_PACK_ROWS) else 0
@@ -187,6 +235,8 @@ class MaxMeanSimilarity(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _gidx):
         q, v, T, scale, idx, clip = ctx.saved_tensors
+        if g is None:
+            return None, None, None, None, None
         need_dq, need_dv, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dq, dv, dT = maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq, need_dv, need_dT, flags=ctx.bwd_flags)
         if dT is not None and ctx.t_shape is not None:
@@ -217,3 +267,38 @@ class SymmetricInfoNCE(torch.autograd.Function):
     def backward(ctx, gl, _gs):
         (g,) = ctx.saved_tensors
         return g * gl
+
+
+class ContrastiveHead(torch.autograd.Function):
+    """(contrastive, l_cal, contrastive + l_cal, sums) from the fp32 clip matrix and the temperature parameter:
+    symmetric InfoNCE (src/model.py:453-459 / :572-578), its statistics sums and the temperature-calibration term
+    20*relu(-log T)^2 (model.py:420-427) in two launches (triad_contrastive_head).  `temperature` may be None
+    (no calibration term: the text-visual loss, model.py:544-593, has none)."""
+
+    @staticmethod
+    def forward(ctx, clip, temperature):
+        clip = clip.contiguous()
+        if clip.dtype != torch.float32:
+            clip = clip.float()
+        B = clip.shape[0]
+        if clip.dim() != 2 or clip.shape[1] != B:
+            raise ValueError("InfoNCE needs a square clip-similarity matrix")
+        T = temperature_tensor(temperature, clip.device) if temperature is not None else None
+        g, sums, out = contrastive_head(clip, T)
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero tensors to add
+        ctx.save_for_backward(g, out)
+        ctx.t_meta = (temperature.shape, temperature.dtype) if isinstance(temperature, torch.Tensor) else None
+        ctx.mark_non_differentiable(sums)
+        return out[0], out[1], out[2], sums
+
+    @staticmethod
+    def backward(ctx, g_con, g_cal, g_tot, _gs):
+        g, out = ctx.saved_tensors
+        up = g_con if g_tot is None else (g_tot if g_con is None else g_con + g_tot)
+        dclip = g * up if (up is not None and ctx.needs_input_grad[0]) else None
+        dT = None
+        if ctx.t_meta is not None and ctx.needs_input_grad[1]:
+            upc = g_cal if g_tot is None else (g_tot if g_cal is None else g_cal + g_tot)
+            if upc is not None:
+                dT = (out[3] * upc).reshape(ctx.t_meta[0]).to(ctx.t_meta[1])
+        return dclip, dT

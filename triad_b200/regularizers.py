@@ -35,10 +35,11 @@ def nonneg_chunk(S: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write
     ops._require_cuda(S, T, sums)
     if not S.is_contiguous():
         raise ValueError("nonneg_chunk needs a contiguous chunk")
-    ws = ops._Workspace.get(lib.triad_nonneg_workspace_bytes(), S.device, "nonneg")
-    check(lib.triad_nonneg_chunk(S.data_ptr(), S.numel(), ops._dtype_code(S), T.data_ptr(), float(lo), float(coef),
-                                 1 if write_grad else 0, sums.data_ptr(), ws.data_ptr(), ws.numel(),
-                                 ops._stream()), "triad_nonneg_chunk")
+    with ops._on(S):
+        ws = ops._Workspace.get(lib.triad_nonneg_workspace_bytes(), S.device, "nonneg")
+        check(lib.triad_nonneg_chunk(S.data_ptr(), S.numel(), ops._dtype_code(S), T.data_ptr(), float(lo), float(coef),
+                                     1 if write_grad else 0, sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     ops._stream(S.device)), "triad_nonneg_chunk")
 
 
 #: use the fused tcgen05 forward (triad_nonneg_fused_chunk) when the shape allows; False forces the library-GEMM +
@@ -59,10 +60,12 @@ def nonneg_fused_chunk(q: torch.Tensor, vc: torch.Tensor, T: torch.Tensor, lo: f
     Bq, Nq, D = q.shape
     jc, Nv, _ = vc.shape
     N = torch.empty(Bq * Nq, jc * Nv, dtype=torch.bfloat16, device=q.device) if write_grad else None
-    ws = ops._Workspace.get(lib.triad_nonneg_fused_workspace_bytes(), q.device, "nonneg_fused")
-    check(lib.triad_nonneg_fused_chunk(q.data_ptr(), vc.data_ptr(), T.data_ptr(), Bq, jc, Nq, Nv, D, float(lo), float(coef),
-                                       None if N is None else N.data_ptr(), jc * Nv, 1 if write_grad else 0,
-                                       sums.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()), "triad_nonneg_fused_chunk")
+    with ops._on(q):
+        ws = ops._Workspace.get(lib.triad_nonneg_fused_workspace_bytes(), q.device, "nonneg_fused")
+        check(lib.triad_nonneg_fused_chunk(q.data_ptr(), vc.data_ptr(), T.data_ptr(), Bq, jc, Nq, Nv, D, float(lo), float(coef),
+                                           None if N is None else N.data_ptr(), jc * Nv, 1 if write_grad else 0,
+                                           sums.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream(q.device)),
+              "triad_nonneg_fused_chunk")
     return N
 
 

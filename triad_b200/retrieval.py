@@ -31,10 +31,11 @@ def _scores(q_feats: torch.Tensor, v_feats: torch.Tensor, temperature, direction
     T = ops.temperature_tensor(temperature, q.device)
     out = torch.empty(n_img, dtype=torch.float32, device=q.device)
     nws = lib.triad_retrieve_workspace_bytes(Nq, n_img, Nv, D, dt)
-    ws = ops._Workspace.get(nws, q.device, "retrieve")
-    check(lib.triad_retrieve_scores(q.data_ptr(), Nq, gal.data_ptr(), n_img, Nv, D, dt, T.data_ptr(), 1, direction,
-                                    out.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream()),
-          "triad_retrieve_scores")
+    with ops._on(q):
+        ws = ops._Workspace.get(nws, q.device, "retrieve")
+        check(lib.triad_retrieve_scores(q.data_ptr(), Nq, gal.data_ptr(), n_img, Nv, D, dt, T.data_ptr(), 1, direction,
+                                        out.data_ptr(), ws.data_ptr(), ws.numel(), ops._stream(q.device)),
+              "triad_retrieve_scores")
     return out
 
 
@@ -66,9 +67,10 @@ def retrieve_topk(q_feats: torch.Tensor, gallery: torch.Tensor, temperature, k: 
     out_s = torch.empty(k, dtype=torch.float32, device=s.device)
     out_i = torch.empty(k, dtype=torch.int32, device=s.device)
     nws = lib.triad_topk_workspace_bytes(n, k)
-    ws = ops._Workspace.get(nws, s.device, "topk")
-    check(lib.triad_topk(s.data_ptr(), n, k, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(),
-                         ops._stream()), "triad_topk")
+    with ops._on(s):
+        ws = ops._Workspace.get(nws, s.device, "topk")
+        check(lib.triad_topk(s.data_ptr(), n, k, out_s.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(),
+                             ops._stream(s.device)), "triad_topk")
     return out_s, out_i
 
 
@@ -109,7 +111,8 @@ def compute_recall_at_k(sim_matrix) -> Dict[str, float]:
         sim = sim_matrix.detach().float().contiguous()
     N = sim.shape[0]
     ranks = torch.empty(N, dtype=torch.int32, device=sim.device)
-    check(lib.triad_diag_ranks(sim.data_ptr(), N, ranks.data_ptr(), ops._stream()), "triad_diag_ranks")
+    with ops._on(sim):
+        check(lib.triad_diag_ranks(sim.data_ptr(), N, ranks.data_ptr(), ops._stream(sim.device)), "triad_diag_ranks")
     r = ranks.cpu().numpy()
     return {"r1": float(np.mean(r < 1)), "r5": float(np.mean(r < 5)),
             "r10": float(np.mean(r < 10)), "r20": float(np.mean(r < 20))}
