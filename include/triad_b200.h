@@ -146,6 +146,8 @@ int triad_contrastive_head(const float* clip, int B, const float* temperature,
 #define TRIAD_BWD_NO_PREFETCH  4   /* tiled dq without the prefetch.global.L1 look-ahead (A/B timing)      */
 #define TRIAD_BWD_PACK_ROWS   32   /* dq sweeps only the rows whose row_scale is non-zero (masked text tokens
                                       get an exact zero gradient without being gathered for)                */
+#define TRIAD_BWD_UNIFORM_SCALE 128  /* the caller guarantees row_scale has no zeros (no attention mask): the dv sort then
+                                      does not read it per row to decide which rows to list                            */
 #define TRIAD_BWD_DQ_STAGED    64   /* dq: the round-1 kernel (winners/weights staged through shared memory) — cross-check */
 size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
 int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,

@@ -36,7 +36,7 @@ def _worker(rank, world, port, masked, ret, pipelined=False):
                                        kernels=PipelinedOracleKernels() if pipelined else OracleKernels())
         stats = stats_from_all_sums(out["all_sums"], B, "av")
         ret[rank] = {"loss": out["loss"].item(), "dq": out["dq"], "dv": out["dv"], "dT": out["dT"].item(),
-                     "stats": stats}
+                     "dT_global": out["dT_global"].item(), "stats": stats}
     finally:
         dist.destroy_process_group()
 
@@ -58,11 +58,18 @@ def test_two_rank_step_matches_full_batch(masked, pipelined):
     for r in range(world):
         o = ret[r]
         assert abs(o["loss"] - ref["loss"].item()) < 1e-5
-        assert abs(o["dT"] - ref["dT"].item()) < 1e-6
+        assert abs(o["dT_global"] - ref["dT"].item()) < 1e-6
         assert torch.allclose(o["dq"].double(), ref["dq"][r * Bl:(r + 1) * Bl], atol=1e-7)
         assert torch.allclose(o["dv"].double(), ref["dv"][r * Bl:(r + 1) * Bl], atol=1e-7)
         for k, val in st.items():
             assert abs(o["stats"][k] - val) < 1e-5, k
+    # the temperature is replicated: every rank returns its SHARE, like the gradients that reach replicated encoder
+    # weights through dq / dv — a SUM over ranks is the global gradient (and the shares are not all equal)
+    assert abs(sum(ret[r]["dT"] for r in range(world)) - ref["dT"].item()) < 1e-6
+    g, clip = ref["g"].double(), ref["clip"].double()
+    for r in range(world):
+        share = (g[r * Bl:(r + 1) * Bl] * clip[r * Bl:(r + 1) * Bl]).sum().item() / 1.5
+        assert abs(ret[r]["dT"] - share) < 1e-6
 
 
 def test_single_process_path():
@@ -116,8 +123,9 @@ def test_two_rank_regularisers_match_full_batch(kind):
     for r in range(world):
         o = ret[r]
         assert abs(o["reg"] - reg.item()) < 1e-5 * abs(reg.item())
-        assert abs(o["dT"] - T64.grad.item()) < 1e-4 * abs(T64.grad.item())
+        assert abs(o["dT_global"] - T64.grad.item()) < 1e-4 * abs(T64.grad.item())
         assert torch.allclose(o["dq"].double(), q64.grad[r * Bl:(r + 1) * Bl], rtol=1e-4, atol=1e-7)
         assert torch.allclose(o["dv"].double(), v64.grad[r * Bl:(r + 1) * Bl], rtol=1e-4, atol=1e-7)
         if kind == "av":
             assert abs(o["smooth"] - smooth.item()) < 1e-5 * abs(smooth.item())
+    assert abs(sum(ret[r]["dT"] for r in range(world)) - T64.grad.item()) < 1e-4 * abs(T64.grad.item())

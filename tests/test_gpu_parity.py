@@ -134,7 +134,7 @@ def test_golden_total_loss_with_regularisers(case, chunk_bytes, fused, monkeypat
     else:
         clip, tok = m.compute_all_similarities_tv(qd, vd, mask.cuda())
         total, stats = m.compute_contrastive_loss_tv(clip, tok)
-        con = m._contrastive(clip, tok, "tv")[0]
+        con = m._loss_head(clip, tok, "tv", False)[0]
         reg = total - con
     fp32 = case.dtype == "fp32"
     tol = 1e-4 if fp32 else 1e-2
@@ -313,7 +313,7 @@ def test_backward_variants_agree(masked):
     rdq, rdv, _ = O.maxmean_backward(q, v, idx_ref_layout, g.cpu(), 1.5, ref["row_scale"], clip.cpu())
     ref = {"dq": rdq, "dv": rdv}
     outs = {}
-    for name, flags, f32 in (("default", 0, False), ("dq_l1", _lib.BWD_DQ_L1, False),
+    for name, flags, f32 in (("default", 0, False), ("dq_staged", _lib.BWD_DQ_STAGED, False), ("dq_l1", _lib.BWD_DQ_L1, False),
                              ("dq_l1_nopf", _lib.BWD_DQ_L1 | _lib.BWD_NO_PREFETCH, False),
                              ("dq_generic", _lib.BWD_GENERIC_DQ, False),
                              ("dq_packed", _lib.BWD_PACK_ROWS, False),
@@ -325,7 +325,7 @@ def test_backward_variants_agree(masked):
         outs[name] = (dq, dv)
         assert rel_err(dq.cpu(), ref["dq"]) < 4e-3, name
         assert rel_err(dv.cpu(), ref["dv"]) < (1e-5 if f32 else 4e-3), name
-    for name in ("dq_l1", "dq_l1_nopf", "dq_generic", "dq_packed"):          # same summation order: bit-identical
+    for name in ("dq_staged", "dq_l1", "dq_l1_nopf", "dq_generic", "dq_packed"):   # same summation order: bit-identical
         assert torch.equal(outs[name][0], outs["default"][0]), name
     assert torch.equal(outs["dv_generic"][1], outs["default"][1])             # grouped vs global sort: same lists
     assert torch.equal(outs["dv_blocks_generic"][1], outs["dv_blocks"][1])
@@ -553,3 +553,66 @@ def test_errors_are_loud():
         m.compute_all_similarities_av(torch.randn(2, 3, 64).cuda().half(), torch.randn(2, 5, 64).cuda().half())
     with pytest.raises(TriadError):
         m.compute_all_similarities_av(torch.randn(2, 3, 60).cuda(), torch.randn(2, 5, 60).cuda())  # D % 8
+
+
+@pytest.mark.parametrize("B", [1, 2, 7, 33, 256, 600])
+def test_fused_head_matches_the_block_kernels(B):
+    """triad_contrastive_head (2 launches: InfoNCE + statistics + temperature-calibration term) is bit-identical to
+    the partial/finish pair the sharded path uses, and its scalars are the reference's (model.py:420-427, :453-459)."""
+    from triad_b200 import ops
+    gen = torch.Generator().manual_seed(B)
+    clip = (torch.randn(B, B, generator=gen) * 2).cuda()
+    for T in (1.5, 0.8):
+        Tt = torch.tensor(T, device="cuda")
+        g, sums, out = ops.contrastive_head(clip, Tt)
+        row_lse, col_part = ops.infonce_partial(clip, B, 0)
+        g2, sums2 = ops.infonce_finish(clip, B, 0, row_lse, col_part.reshape(1, 2, B))
+        assert torch.equal(g, g2)
+        assert torch.equal(sums[:7], sums2[:7])
+        nce = O.infonce(clip.cpu())
+        assert abs(out[0].item() - nce["loss"].item()) <= 1e-6 * abs(nce["loss"].item())
+        T64 = torch.tensor(T, dtype=torch.float64, requires_grad=True)
+        cal = 20.0 * torch.clamp(-torch.log(T64), min=0) ** 2
+        cal.backward()
+        assert abs(out[1].item() - cal.item()) <= 1e-6 * max(cal.item(), 1e-30)
+        assert abs(out[2].item() - (out[0].item() + out[1].item())) <= 1e-6 * abs(out[2].item())
+        assert abs(out[3].item() - T64.grad.item()) <= 1e-6 * max(abs(T64.grad.item()), 1e-30)
+    g, sums, out = ops.contrastive_head(clip, None)
+    assert out[1].item() == 0.0 and out[3].item() == 0.0
+
+
+def test_loss_uses_the_clip_sims_argument():
+    """compute_contrastive_loss_* compute the loss from the clip_sims ARGUMENT (model.py:430, :544): the matrix the
+    similarity call returned maps to the handle's fp32 copy, an edited one is honoured as given."""
+    B, Nq, Nv, D = 6, 20, 64, 64
+    q, v, _ = O.make_inputs(B, Nq, Nv, D, torch.bfloat16, seed=3)
+    m = _model(1.5)
+    qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+    clip, tok = m.compute_all_similarities_av(qd, vd)
+    base = m.compute_contrastive_loss_av(clip, tok)[1]
+    edited = clip.float() * 0.5
+    con = m.compute_contrastive_loss_av(edited, tok)[1]
+    want = O.infonce(edited.detach().cpu())["loss"]
+    assert abs(con.item() - want.item()) <= 1e-5 * abs(want.item())
+    assert abs(con.item() - base.item()) > 1e-3                      # really a different loss
+    con.backward()                                                   # gradients flow through the edit
+    ref = O.contrastive_step_closed_form(q, v, 1.5)
+    g_half = O.infonce(edited.detach().cpu())["g"] * 0.5
+    dq, dv, _ = O.maxmean_backward(q, v, ref["idx"], g_half.float(), 1.5, ref["row_scale"], ref["clip"])
+    assert rel_err(qd.grad.double().cpu(), dq) < 1e-2 and rel_err(vd.grad.double().cpu(), dv) < 1e-2
+
+
+def test_stats_mapping_behaves_like_the_reference_dict():
+    import copy
+    import json
+    import pickle
+    q, v, _ = O.make_inputs(4, 10, 32, 64, torch.bfloat16, seed=9)
+    m = _model(1.5)
+    clip, tok = m.compute_all_similarities_av(q.cuda(), v.cuda())
+    stats = m.compute_contrastive_loss_av(clip, tok)[4]
+    d = {}
+    d.update(stats)                                                  # train.py:1080
+    assert sorted(d) == sorted(stats.keys()) and len(d) == 6
+    assert all(k in stats for k in d) and {**stats} == d
+    assert json.loads(json.dumps(stats.to_dict())) == d
+    assert pickle.loads(pickle.dumps(stats)) == d and copy.deepcopy(stats) == d

@@ -63,6 +63,9 @@ if __name__ == "__main__":
     if os.environ.get("DQ_AB_CHILD"):
         child()
     else:
-        for v in (sys.argv[1:] or ["0", "1", "2", "3"]):
+        for v in (sys.argv[1:] or ["0", "1", "2", "3", "4"]):
             env = dict(os.environ, DQ_AB_CHILD="1", TRIAD_DQ_VARIANT=v)
-            subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False, timeout=600)
+            try:
+                subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, check=False, timeout=150)
+            except subprocess.TimeoutExpired:
+                print(f"v{v} TIMEOUT", flush=True)

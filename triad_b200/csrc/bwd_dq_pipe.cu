@@ -21,10 +21,11 @@
 //   * the gather is SOFTWARE PIPELINED by half an image: the LDS.128s of rows 4..7 of image j are
 //     in flight while rows 0..3 are accumulated, and rows 0..3 of image j+1 (whose barrier is
 //     tested in between) while rows 4..7 are — a warp never waits for its own loads.
-//   * a dedicated PRODUCER warp issues the TMA loads (setmaxnreg moves its registers to the 16
-//     consumer warps: 120 each).  With the refill inline in warp 0 (dq3) that warp blocked on the
-//     slowest warp's release every image, which tied all warps to within one image of each other;
-//     here consumers drift freely across the ring (kVS - 1 images).
+//   * the ring is refilled WITHOUT tying the warps together.  In dq3 warp 0 refilled the slot image j-1 used
+//     while at image j, so it blocked on the slowest warp's release every image and all warps ran within
+//     one image of each other.  Here either a dedicated producer warpgroup streams the slices
+//     (setmaxnreg: 24 registers for it, 112 for the consumers) or warp 0 refills the slot image j-kLag
+//     used (kLag = 2: its wait blocks only if some warp is more than two images behind).
 //   * the pipeline watchdog no longer votes: a timed-out wait marks the launch (abort flag) and the
 //     kernel finishes with NaNs in dq, so a pipeline bug is LOUD downstream instead of silent.
 //
@@ -39,7 +40,8 @@ using namespace ptx;
 
 constexpr int kGroupsPerTile = 64;                  // 8-row groups per CTA = 512 padded rows
 constexpr int kConsumerWarps = 16;
-constexpr int kThreads = (kConsumerWarps + 4) * 32; // + one producer warpgroup (one lane of it works)
+constexpr int kThreadsWG = (kConsumerWarps + 4) * 32;   // producer-warpgroup mode: + 4 warps (one lane of them works)
+constexpr int kThreadsIn = kConsumerWarps * 32;          // in-warp refill mode
 constexpr int kSlice = 64;                          // bf16 elements of D per CTA (one 128-byte line)
 constexpr int kMaxNv = 256;
 constexpr uint32_t kStageBytes = kMaxNv * kSlice * 2;   // 32 KB per image slice
@@ -108,8 +110,13 @@ struct Params {
     int Bq, Bv, Nq, Nv, D, nq_pad, gq;     // gq = ceil(Nq / 8) groups per query
 };
 
-template <int kVS, bool kDp4a>
-__global__ void __launch_bounds__(kThreads, 1)
+// kLag == 0: a dedicated producer warpgroup streams the V slices (640 threads; setmaxnreg gives the consumers 112
+//            registers — 512*112 + 128*24 is exactly the 640*96 the CTA is launched with).
+// kLag >= 1: 512 threads, 128 registers; warp 0 refills the ring itself, but the slot it refills at image j is the
+//            one image j-kLag used: its (guarded) wait on that slot's release only blocks when some warp is more
+//            than kLag images behind warp 0, so the warps still drift freely; look-ahead = kVS - kLag images.
+template <int kVS, bool kDp4a, int kLag, int kRowsPerStep>
+__global__ void __launch_bounds__(kLag == 0 ? kThreadsWG : kThreadsIn, 1)
 dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     const int n_groups = p.glist ? *p.n_groups : p.Bq * p.gq;
     if ((int)blockIdx.y * kGroupsPerTile >= n_groups) return;
@@ -134,11 +141,12 @@ dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     }
     __syncthreads();                                   // the only CTA-wide barrier
 
-    if (warp >= kConsumerWarps) {
+    const uint32_t stage_tx = (uint32_t)p.Nv * (kSlice * 2);
+    if constexpr (kLag == 0) {
+      if (warp >= kConsumerWarps) {
         // ---- producer warpgroup: hands its registers to the consumers; one lane streams the V slices ----
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == kConsumerWarps && lane == 0) {
-            const uint32_t stage_tx = (uint32_t)p.Nv * (kSlice * 2);
             int s = 0;
             uint32_t par = 1;                          // parity of the consumers' PREVIOUS release of slot s
             for (int j = 0; j < Bv; ++j) {
@@ -149,8 +157,16 @@ dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
             }
         }
         return;
+      }
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    } else {
+        if (tid == 0) {                                  // prologue: the whole ring
+            for (int j = 0; j < kVS && j < Bv; ++j) {
+                mbar_expect_tx(bar_full + 8 * j, stage_tx);
+                tma_load_3d<1>(sbase + j * kStageBytes, &tmap_v, bar_full + 8 * j, slice * kSlice, 0, j);
+            }
+        }
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
 
     // ---- consumer: 8-lane group gi owns 8 consecutive padded rows of one query; lane c owns 8 elements ----
     const int gi = warp * 4 + (lane >> 3), c = lane & 7;
@@ -162,8 +178,6 @@ dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
         else { qi = k / p.gq; a0 = (k - qi * p.gq) * 8; }
     }
     const size_t pitch = (size_t)p.Bq * p.nq_pad;
-    const uint8_t* ip = p.idx + (size_t)qi * p.nq_pad + a0;       // winners of this group in image 0
-    const float* gp = p.g + (size_t)qi * Bv;
     const uint32_t lane_base = sbase + (uint32_t)c * 16u;
     const bool lane0 = lane == 0;
 
@@ -174,34 +188,59 @@ dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
         for (int e = 0; e < 4; ++e) acc[r][e] = make_float2(0.f, 0.f);
 
     // Winners / weight of images j and j+1 live in two register sets that alternate with the parity of j; the
-    // request for image j+2 goes into the set image j has just finished with (winners: right after the second
-    // half's addresses are formed; weight: after the last FMA), so there is no third set and no register moves.
+    // request for image j+2 goes into the set image j has just finished with (winners: right after the last
+    // addresses of image j are formed; weight: after the last FMA), so there is no third set and no register moves.
+    // Addresses are a uniform 64-bit base (advanced by one image per image) plus a 32-bit per-lane offset.
     const int last = Bv - 1;
-    uint2 W0 = ldg64(ip), W1 = ldg64(ip + (size_t)(last < 1 ? last : 1) * pitch);
-    float w0 = ldg32f(gp), w1 = ldg32f(gp + (last < 1 ? last : 1));
-    const uint8_t* ip2 = ip + 2 * pitch;                   // winners of image j+2 (dereferenced only while j+2 <= last)
-    const float* gp2 = gp + 2;                             // weight of image j+2
+    const uint32_t x0 = (uint32_t)(qi * p.nq_pad + a0);    // < 2^31 (checked by the launcher)
+    const uint8_t* ibase = p.idx;                          // uniform: winners of image j+2 start at ibase + x0
+    const float* gbase = p.g;                              // uniform: weight of image j+2 is gbase[goff]
+    const uint32_t goff = (uint32_t)qi * (uint32_t)Bv;
+    uint2 W0 = ldg64(ibase + x0), W1 = ldg64(ibase + (size_t)(last < 1 ? last : 1) * pitch + x0);
+    float w0 = ldg32f(gbase + goff), w1 = ldg32f(gbase + goff + (last < 1 ? last : 1));
+    ibase += 2 * pitch;
+    gbase += 2;
 
     wait_guarded(bar_full, 0, p.abort_flag, 11);
-    uint4 dA[4], dB[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) dA[r] = lds128(row_addr<kDp4a>(W0.x, r, lane_base));
-
     uint32_t cur = lane_base;                              // this lane's base inside the slot of image j
     uint32_t fbar = bar_full;                              // full barrier of image j's slot (empty = +8*kVS)
     uint32_t par = 0;                                      // parity of image j's slot
-    const uint32_t ring_end = lane_base + kVS * kStageBytes;
+    int slot = 0;
+    // in-warp refill (kLag > 0, warp 0): next image to load, its slot, that slot's full barrier, and the parity of the
+    // release that frees it
+    int jfill = kVS;
+    uint32_t rdst = sbase, rbar = bar_full, rpar = 0;
     auto advance = [&]() {
         cur += kStageBytes; fbar += 8;
-        if (cur == ring_end) { cur = lane_base; fbar = bar_full; par ^= 1u; }
+        if (++slot == kVS) { slot = 0; cur = lane_base; fbar = bar_full; par ^= 1u; }
     };
+#define TRIAD_DQ_REFILL()                                                                                \
+        if (kLag > 0 && warp == 0 && jfill < Bv) {                                                       \
+            if (jfill - kVS + kLag <= j) { /* the slot of image jfill - kVS: released by all warps? */     \
+                wait_guarded(rbar + 8 * kVS, rpar, p.abort_flag, 12);                                    \
+                if (lane0) {                                                                             \
+                    mbar_expect_tx(rbar, stage_tx);                                                      \
+                    tma_load_3d<1>(rdst, &tmap_v, rbar, slice * kSlice, 0, jfill);                       \
+                }                                                                                        \
+                ++jfill; rdst += kStageBytes; rbar += 8;                                                 \
+                if (rdst == sbase + kVS * kStageBytes) { rdst = sbase; rbar = bar_full; rpar ^= 1u; }    \
+            }                                                                                            \
+        }
+
+    int j = 0;
+    if constexpr (kRowsPerStep == 4) {
+        // ---- half-image pipelining: two 4-row buffers (32 registers) ----
+        uint4 dA[4], dB[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) dA[r] = lds128(row_addr<kDp4a>(W0.x, r, lane_base));
 // One image.  HAS_NEXT: image j+1 exists (its first half is requested in the middle); PREFETCH: image j+2 exists.
 #define TRIAD_DQ_IMAGE(Wc, wc, Wn, HAS_NEXT, PREFETCH)                                                   \
     {                                                                                                    \
         _Pragma("unroll") for (int r = 0; r < 4; ++r) dB[r] = lds128(row_addr<kDp4a>(Wc.y, r, cur));     \
-        if (PREFETCH) { Wc = ldg64(ip2); ip2 += pitch; }                                                 \
+        if (PREFETCH) { Wc = ldg64(ibase + x0); ibase += pitch; }                                        \
         _Pragma("unroll") for (int r = 0; r < 4; ++r) fma_row(acc[r], wc, dA[r]);                        \
         const uint32_t ebar = fbar + 8 * kVS;                                                            \
+        TRIAD_DQ_REFILL()                                                                                \
         if (HAS_NEXT) {                                                                                  \
             advance();                                                                                   \
             wait_guarded(fbar, par, p.abort_flag, 11);                                                   \
@@ -210,19 +249,56 @@ dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
         _Pragma("unroll") for (int r = 0; r < 4; ++r) fma_row(acc[4 + r], wc, dB[r]);                    \
         __syncwarp();                                                                                    \
         if (lane0) mbar_arrive_local(ebar);                                                              \
-        if (PREFETCH) { wc = ldg32f(gp2); ++gp2; }                                                       \
+        if (PREFETCH) { wc = ldg32f(gbase + goff); ++gbase; }                                            \
     }
-
-    int j = 0;
-    for (; j + 3 <= last; j += 2) {                        // both images of the pair have a successor two ahead
-        TRIAD_DQ_IMAGE(W0, w0, W1, true, true)
-        TRIAD_DQ_IMAGE(W1, w1, W0, true, true)
-    }
-    for (; j <= last; ++j) {                               // the last two or three images
-        if (j & 1) TRIAD_DQ_IMAGE(W1, w1, W0, j < last, j + 2 <= last)
-        else TRIAD_DQ_IMAGE(W0, w0, W1, j < last, j + 2 <= last)
-    }
+        for (; j + 3 <= last; j += 2) {                    // both images of the pair have a successor two ahead
+            TRIAD_DQ_IMAGE(W0, w0, W1, true, true)
+            TRIAD_DQ_IMAGE(W1, w1, W0, true, true)
+        }
+        for (; j <= last; ++j) {                           // the last two or three images
+            if (j & 1) TRIAD_DQ_IMAGE(W1, w1, W0, j < last, j + 2 <= last)
+            else TRIAD_DQ_IMAGE(W0, w0, W1, j < last, j + 2 <= last)
+        }
 #undef TRIAD_DQ_IMAGE
+    } else {
+        // ---- quarter-image pipelining: two 2-row buffers (16 registers): rows 2k..2k+1 are accumulated while rows
+        //      2k+2..2k+3 are in flight; the first pair of image j+1 is requested before the last pair of image j
+        //      is consumed.  16 registers less than the half-image form: no spills at 112 registers. ----
+        uint4 dX[2], dY[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) dX[r] = lds128(row_addr<kDp4a>(W0.x, r, lane_base));
+#define TRIAD_DQ_IMAGE(Wc, wc, Wn, HAS_NEXT, PREFETCH)                                                       \
+    {                                                                                                        \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) dY[r] = lds128(row_addr<kDp4a>(Wc.x, 2 + r, cur));     \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) fma_row(acc[r], wc, dX[r]);                            \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) dX[r] = lds128(row_addr<kDp4a>(Wc.y, r, cur));         \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) fma_row(acc[2 + r], wc, dY[r]);                        \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) dY[r] = lds128(row_addr<kDp4a>(Wc.y, 2 + r, cur));     \
+        if (PREFETCH) { Wc = ldg64(ibase + x0); ibase += pitch; }                                            \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) fma_row(acc[4 + r], wc, dX[r]);                        \
+        const uint32_t ebar = fbar + 8 * kVS;                                                                \
+        TRIAD_DQ_REFILL()                                                                                    \
+        if (HAS_NEXT) {                                                                                      \
+            advance();                                                                                       \
+            wait_guarded(fbar, par, p.abort_flag, 11);                                                       \
+            _Pragma("unroll") for (int r = 0; r < 2; ++r) dX[r] = lds128(row_addr<kDp4a>(Wn.x, r, cur));     \
+        }                                                                                                    \
+        _Pragma("unroll") for (int r = 0; r < 2; ++r) fma_row(acc[6 + r], wc, dY[r]);                        \
+        __syncwarp();                                                                                        \
+        if (lane0) mbar_arrive_local(ebar);                                                                  \
+        if (PREFETCH) { wc = ldg32f(gbase + goff); ++gbase; }                                                \
+    }
+        for (; j + 3 <= last; j += 2) {
+            TRIAD_DQ_IMAGE(W0, w0, W1, true, true)
+            TRIAD_DQ_IMAGE(W1, w1, W0, true, true)
+        }
+        for (; j <= last; ++j) {
+            if (j & 1) TRIAD_DQ_IMAGE(W1, w1, W0, j < last, j + 2 <= last)
+            else TRIAD_DQ_IMAGE(W0, w0, W1, j < last, j + 2 <= last)
+        }
+#undef TRIAD_DQ_IMAGE
+    }
+#undef TRIAD_DQ_REFILL
 
     // ---- epilogue: scale, round to bf16, one 16-byte store per row and lane (128 B per row and group) ----
     const bool poisoned = *(volatile int*)p.abort_flag != 0;   // a timed-out wait anywhere in the grid: make it loud
@@ -249,9 +325,10 @@ dq_pipe_kernel(const __grid_constant__ CUtensorMap tmap_v, const Params p) {
     }
 }
 
-template <int kVS, bool kDp4a>
+template <int kVS, bool kDp4a, int kLag, int kRowsPerStep>
 static int launch_t(const CUtensorMap& mv, const Params& p, int max_groups, cudaStream_t st) {
-    auto kern = dq_pipe_kernel<kVS, kDp4a>;
+    auto kern = dq_pipe_kernel<kVS, kDp4a, kLag, kRowsPerStep>;
+    constexpr int kThreads = kLag == 0 ? kThreadsWG : kThreadsIn;
     TRIAD_SET_MAX_SMEM(kern, smem_bytes<kVS>());
     const dim3 grid((unsigned)(p.D / kSlice), (unsigned)ceil_div(max_groups, kGroupsPerTile));
     kern<<<grid, kThreads, smem_bytes<kVS>(), st>>>(mv, p);
@@ -282,11 +359,15 @@ int launch_dq_pipe(const void* v, const void* idx, const float* g, const float* 
     p.Bq = Bq; p.Bv = Bv; p.Nq = Nq; p.Nv = Nv; p.D = D; p.nq_pad = nq_padded(Nq); p.gq = ceil_div(Nq, 8);
     const int max_groups = Bq * p.gq;
     if (glist) TRIAD_CUDA_CHECK(cudaMemsetAsync(dq, 0, (size_t)Bq * Nq * D * 2, st));   // rows of inactive groups: zero gradient
+    if ((long long)Bq * p.nq_pad > 0x7fffffffLL || (long long)Bq * Bv > 0x7fffffffLL)
+        return fail_msg(TRIAD_ERR_BAD_SHAPE, "dq_pipe: Bq*nq_pad and Bq*Bv must fit in 31 bits");
     switch (variant) {
-        case 1: return launch_t<6, true>(mv, p, max_groups, st);
-        case 2: return launch_t<5, true>(mv, p, max_groups, st);
-        case 3: return launch_t<7, false>(mv, p, max_groups, st);
-        default: return launch_t<7, true>(mv, p, max_groups, st);
+        // measured at cfg 2 (B=256, 250x256, D=512; round-1 staged kernel 1.045 ms): see DESIGN.md K3a
+        case 1: return launch_t<7, true, 2, 4>(mv, p, max_groups, st);     // in-warp refill two images behind, 128 registers
+        case 2: return launch_t<7, true, 0, 4>(mv, p, max_groups, st);     // producer warpgroup, half-image pipelining (spills at 112)
+        case 3: return launch_t<6, true, 0, 2>(mv, p, max_groups, st);     // 6-deep ring
+        case 4: return launch_t<7, true, 2, 2>(mv, p, max_groups, st);     // in-warp refill, quarter-image pipelining
+        default: return launch_t<7, true, 0, 2>(mv, p, max_groups, st);    // producer warpgroup, quarter-image pipelining
     }
 }
 

@@ -62,6 +62,20 @@ static inline PartLayout part_layout(int M, int Nq) {
     PartLayout p; p.G = ceil_div(M, 32); p.S = 31 / Nq + 2; return p;
 }
 
+// ---- division by a runtime constant (n < 2^31, 1 <= d < 2^31): one multiply-high and a shift -----------
+struct FastDiv {
+    uint32_t d, mul, shift;      // n / d == umulhi(n, mul) >> shift   (round-up method, exact for n < 2^31)
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f; f.d = d;
+    if (d <= 1) { f.mul = 0; f.shift = 0; return f; }            // handled separately (n / 1)
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                                   // l = ceil(log2 d)
+    f.shift = l - 1;                                               // n < 2^31: a 32-bit multiplier with shift l-1 is exact
+    f.mul = (uint32_t)((((1ull << (31 + l)) + d - 1) / d) & 0xffffffffull);
+    return f;
+}
+
 // ---- argmax index layout ------------------------------------------------------------------
 // idx[j][i][a], a < nq_pad = Nq rounded up to 16: every query's run of winners starts 16-byte
 // aligned, so the backward can fetch 8 or 16 consecutive rows' winners with one vector load.
@@ -104,6 +118,10 @@ int launch_dq_tile(const void* v, const void* idx, int idx_bytes, const float* g
 
 // ---- device helpers -----------------------------------------------------------------------
 #if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+    return f.d <= 1 ? n : (__umulhi(n, f.mul) >> f.shift);
+}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

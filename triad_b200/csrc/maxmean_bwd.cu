@@ -323,45 +323,61 @@ constexpr int kGroupMaxNv = 1024;
 
 static size_t group_sort_smem(int Nv) { return (size_t)kGroupRows * 2 + (size_t)(kGroupWarps + 2) * Nv * 4 + 16; }
 
+// Rows are walked in the PADDED index space of the argmax buffer (x = i*nq_pad + a): one image's winners are then
+// one contiguous byte string, fetched 16 bytes (16 rows) per lane and load instead of a byte at a time, and the
+// (i, a) of a vector comes from one division.  Pad entries (a >= Nq) and zero-weight rows are simply not listed.
+// ncu on the byte-at-a-time version: 139 us at cfg 2 with the L1/LSU pipe at 74 % — 64 scalar loads per lane.
 template <typename IdxT>
 __global__ void __launch_bounds__(kGroupWarps * 32, 3)
 dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, const float* __restrict__ row_scale,
-                     size_t img_pitch, int j0, int n_groups, int Mb, int Bv, int Nq, int Nv, int nq_pad,
-                     uint32_t* __restrict__ segc, DvEntry* __restrict__ entries) {
+                     const int masked, size_t img_pitch, int j0, int n_groups, int Mpad, int Bv, int Nq, int Nv, int nq_pad,
+                     const FastDiv div_pad, uint32_t* __restrict__ segc, DvEntry* __restrict__ entries) {
     extern __shared__ __align__(16) unsigned char gs_smem[];
-    uint16_t* sorted = reinterpret_cast<uint16_t*>(gs_smem);                              // [kGroupRows] local row numbers
+    uint16_t* sorted = reinterpret_cast<uint16_t*>(gs_smem);                              // [kGroupRows] local padded row numbers
     uint32_t* hist = reinterpret_cast<uint32_t*>(gs_smem + (size_t)kGroupRows * 2);       // [warps][Nv]
     uint32_t* lbase = hist + kGroupWarps * Nv;                                            // [Nv]
     uint32_t* tot = lbase + Nv;                                                           // [Nv]
     uint32_t* total_s = tot + Nv;
 
+    constexpr int kVec = 16 / (int)sizeof(IdxT);                  // rows per 16-byte load
+    constexpr int kLoads = kGroupPerLane / kVec;                  // loads per lane (32 rows per lane)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int jl = blockIdx.x / n_groups, c = blockIdx.x - jl * n_groups;
     const int j = j0 + jl;
     const int x_group = c * kGroupRows;
     const IdxT* base = idx + (size_t)j * img_pitch;
-    const uint32_t lt = (1u << lane) - 1u;
 
     for (int k = tid; k < kGroupWarps * Nv; k += blockDim.x) hist[k] = 0;
     __syncthreads();
 
-    // ---- 1. every lane fetches its 32 winners (independent loads), then the per-warp histogram.
-    //         Winners are kept packed two per register (0xffff = row absent or zero weight). ----
+    // ---- 1. every lane fetches its 32 winners (kLoads independent vector loads), then the per-warp histogram.
+    //         Winners are kept packed two per register (0xffff = pad entry, row beyond the block, or zero weight).
+    //         Lane's local row of (load v, element e): warp*1024 + v*32*kVec + lane*kVec + e. ----
     uint32_t pv[kGroupPerLane / 2];
     uint32_t* myh = hist + warp * Nv;
     {
-        const int xw = x_group + warp * (kGroupPerLane * 32) + lane;
-        int i = xw / Nq, a = xw - i * Nq;                     // advanced incrementally: +32 rows per step
+        uint4 raw[kLoads];
 #pragma unroll
-        for (int k = 0; k < kGroupPerLane; ++k) {
-            const int x = xw + k * 32;
-            const bool in = x < Mb;                         // two INDEPENDENT loads per row (no load behind a branch)
-            const float rsx = in ? row_scale[x] : 0.f;
-            const uint32_t pp = in ? (uint32_t)base[(size_t)i * nq_pad + a] : 0u;
-            const uint32_t p = (rsx != 0.f) ? pp : 0xffffu;
-            if (k & 1) pv[k >> 1] |= p << 16; else pv[k >> 1] = p;
-            a += 32;
-            while (a >= Nq) { a -= Nq; ++i; }
+        for (int v = 0; v < kLoads; ++v) {
+            const int x = x_group + warp * (kGroupPerLane * 32) + v * 32 * kVec + lane * kVec;
+            raw[v] = make_uint4(0u, 0u, 0u, 0u);
+            if (x < Mpad) raw[v] = __ldg(reinterpret_cast<const uint4*>(base + x));        // nq_pad % 16 == 0: never straddles
+        }
+#pragma unroll
+        for (int v = 0; v < kLoads; ++v) {
+            const int x = x_group + warp * (kGroupPerLane * 32) + v * 32 * kVec + lane * kVec;
+            const uint32_t qi = fast_div((uint32_t)x, div_pad);
+            const int a0 = x - (int)qi * nq_pad;
+            const uint32_t w32[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+                uint32_t p = sizeof(IdxT) == 1 ? (w32[e >> 2] >> (8 * (e & 3))) & 0xffu : (w32[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+                bool ok = x < Mpad && a0 + e < Nq;
+                if (masked && ok) ok = row_scale[(size_t)qi * Nq + a0 + e] != 0.f;
+                if (!ok) p = 0xffffu;
+                const int k = v * kVec + e;
+                if (k & 1) pv[k >> 1] |= p << 16; else pv[k >> 1] = p;
+            }
         }
 #pragma unroll
         for (int k = 0; k < kGroupPerLane; ++k) {
@@ -392,18 +408,16 @@ dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, 
         if (lane == 0) { *total_s = carry; seg_out[Nv] = carry; }
     }
     __syncthreads();
-    // ---- 3. placement.  Slot = run start + this warp's prefix + a shared-memory atomic counter.  A lane's own
-    //         rows and a warp's successive steps take increasing slots; only rows that meet in the SAME 32-row
-    //         step (or, in principle, reordered atomics) can land out of order, so step 3b sorts every patch's
-    //         run by row — an insertion sort over an almost sorted run of ~Rows/Nv 16-bit values, one thread
-    //         per patch.  (__match_any_sync ranking made this phase 40 % of the kernel: its latency grows with
-    //         the number of distinct keys in the warp, here ~30.) ----
+    // ---- 3. placement.  Slot = run start + this warp's prefix + a shared-memory atomic counter; step 3b sorts every
+    //         patch's run by row (insertion sort over an almost sorted run of ~Rows/Nv 16-bit values, one thread per
+    //         patch), which makes the order "rows ascending" whatever order the atomics resolved in. ----
 #pragma unroll
     for (int k = 0; k < kGroupPerLane; ++k) {
         const uint32_t pk = (pv[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
         if (pk != 0xffffu) {
             const uint32_t slot = lbase[pk] + atomicAdd(&myh[pk], 1u);
-            sorted[slot] = (uint16_t)(warp * (kGroupPerLane * 32) + k * 32 + lane);
+            const int v = k / kVec, e = k - v * kVec;
+            sorted[slot] = (uint16_t)(warp * (kGroupPerLane * 32) + v * 32 * kVec + lane * kVec + e);
         }
     }
     __syncthreads();
@@ -417,14 +431,16 @@ dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, 
         }
     }
     __syncthreads();
-    // ---- 4. the group's list leaves as one contiguous run; the weight is attached here ----
+    // ---- 4. the group's list leaves as one contiguous run; the (unpadded) row number and the weight are attached here ----
     const uint32_t n = *total_s;
     DvEntry* out = entries + (size_t)blockIdx.x * kGroupRows;
+    const float* gj = g + j;
 #pragma unroll 8
     for (uint32_t t = tid; t < n; t += kGroupWarps * 32) {
-        const int x = x_group + (int)sorted[t];
-        const int i = x / Nq;
-        DvEntry d; d.row = (uint32_t)x; d.w = row_scale[x] * g[(size_t)i * Bv + j];
+        const uint32_t x = (uint32_t)x_group + (uint32_t)sorted[t];
+        const uint32_t i = fast_div(x, div_pad);
+        const uint32_t r = x - i * (uint32_t)(nq_pad - Nq);                    // i*Nq + a
+        DvEntry d; d.row = r; d.w = row_scale[r] * gj[(size_t)i * Bv];
         out[t] = d;
     }
 }
@@ -707,21 +723,50 @@ dv_gather_grouped_kernel(const __nv_bfloat16* __restrict__ q, const DvEntry* __r
 }
 
 // ---------------------------------------------------------------------------------------
-// dT = sum g*clip / T : single CTA, fixed-order tree (deterministic)
+// dT = sum g*clip / T.  Up to kDtMaxBlocks CTAs sum contiguous chunks (fp64, fixed order inside a
+// CTA); the last CTA to take a ticket adds the per-CTA partials in CTA order — deterministic, and
+// a B = 8192 rank block (8 M elements) is no longer read by a single SM.
 // ---------------------------------------------------------------------------------------
+constexpr int kDtMaxBlocks = 128;
+constexpr size_t kCtrlBytes = 4096;        // workspace control block: [0] abort flag, [16] dT ticket, [64..] dT partials
+
 __global__ void __launch_bounds__(1024)
-dT_kernel(const float* __restrict__ g, const float* __restrict__ clip, size_t n,
-          const float* __restrict__ Tptr, float* __restrict__ dT) {
+dT_kernel(const float* __restrict__ g, const float* __restrict__ clip, size_t n, size_t per_block,
+          const float* __restrict__ Tptr, float* __restrict__ dT, double* __restrict__ partials,
+          unsigned int* __restrict__ ticket) {
     __shared__ double red[32];
-    double a = 0.0;
-    for (size_t k = threadIdx.x; k < n; k += 1024) a += (double)g[k] * (double)clip[k];
+    __shared__ bool is_last;
+    const size_t k0 = (size_t)blockIdx.x * per_block;
+    const size_t k1 = k0 + per_block < n ? k0 + per_block : n;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;      // four independent chains: the loads of one thread overlap
+    size_t k = k0 + threadIdx.x;
+    for (; k + 3 * 1024 < k1; k += 4 * 1024) {
+        const float g0 = g[k], g1 = g[k + 1024], g2 = g[k + 2048], g3 = g[k + 3072];
+        const float c0 = clip[k], c1 = clip[k + 1024], c2 = clip[k + 2048], c3 = clip[k + 3072];
+        a0 += (double)g0 * (double)c0; a1 += (double)g1 * (double)c1;
+        a2 += (double)g2 * (double)c2; a3 += (double)g3 * (double)c3;
+    }
+    for (; k < k1; k += 1024) a0 += (double)g[k] * (double)clip[k];
+    double a = (a0 + a1) + (a2 + a3);
     a = warp_sum_d(a);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
     __syncthreads();
     if (threadIdx.x < 32) {
         double b = red[threadIdx.x];
         b = warp_sum_d(b);
-        if (threadIdx.x == 0) *dT = (float)(b / (double)*Tptr);
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = b;
+            __threadfence();
+            is_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+        }
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += ((volatile double*)partials)[b];
+        *dT = (float)(t / (double)*Tptr);
+        *ticket = 0u;
     }
 }
 
@@ -749,8 +794,9 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool
     pl.nblk = (int)(((size_t)Bq + qb - 1) / qb);
     pl.scratch = pl.nblk > 1 && !out_f32;
     const size_t Mb = qb * Nq;                                       // rows per block
-    const size_t ng = (Mb + kGroupRows - 1) / kGroupRows;            // sort groups per block (grouped path)
-    const size_t Me = ng * kGroupRows;                               // entry slots per image (>= Mb)
+    const size_t Mp = qb * (size_t)nq_padded(Nq);                    // ... in the padded index space the grouped sort walks
+    const size_t ng = (Mp + kGroupRows - 1) / kGroupRows;            // sort groups per block (grouped path)
+    const size_t Me = ng * kGroupRows > Mb ? ng * kGroupRows : Mb;   // entry slots per image (both sort paths fit)
     size_t jb = ((size_t)1 << 30) / (Me * sizeof(DvEntry));
     if (pl.scratch) {                                                // keep the fp32 scratch <= 256 MB
         const size_t js = ((size_t)256 << 20) / ((size_t)Nv * D * 4);
@@ -759,7 +805,7 @@ static DvPlan dv_plan(int Bq, int Bv, int Nq, int Nv, int D, int elt_bytes, bool
     if (jb < 1) jb = 1;
     if (jb > (size_t)Bv) jb = Bv;
     pl.jb = (int)jb;
-    size_t o = 256;                                       // [0,256): control block (watchdog flag)
+    size_t o = kCtrlBytes;                                // control block (watchdog flag, dT ticket and partials)
     pl.off_cnt = o;     o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_start = o;   o += align_up(jb * kSortGroups * (size_t)Nv * 4, 256);
     pl.off_seg = o;     o += align_up(jb * ((size_t)Nv + 1) * 4, 256);
@@ -851,12 +897,14 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
                 if constexpr (sizeof(T) == 2) {
                     if (Nv <= kGroupMaxNv && !(bwd_flags & TRIAD_BWD_GENERIC_DV)) {
                         // grouped path: shared-memory sort per (image, row group) + gather over the grouped lists
-                        const int n_groups = ceil_div((int)Mb, kGroupRows);
+                        const int Mpad = nq * nq_pad;
+                        const int n_groups = ceil_div(Mpad, kGroupRows);
                         uint32_t* segc = (uint32_t*)((char*)ws + pl.off_segc);
                         auto skern = dv_group_sort_kernel<IdxT>;
                         TRIAD_SET_MAX_SMEM(skern, group_sort_smem(kGroupMaxNv));
                         skern<<<nj * n_groups, kGroupWarps * 32, group_sort_smem(Nv), st>>>(
-                            idx_b, g_b, rs_b, img_pitch, j0, n_groups, (int)Mb, Bv, Nq, Nv, nq_pad, segc, entries);
+                            idx_b, g_b, rs_b, (bwd_flags & TRIAD_BWD_UNIFORM_SCALE) ? 0 : 1, img_pitch, j0, n_groups, Mpad, Bv, Nq, Nv,
+                            nq_pad, make_fastdiv((uint32_t)nq_pad), segc, entries);
                         TRIAD_LAUNCH_CHECK("dv_group_sort_kernel");
                         const __nv_bfloat16* qb16 = (const __nv_bfloat16*)q_b;
                         const bool wide_rows = D > 256;
@@ -922,7 +970,11 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
         }
     }
     if (dT) {
-        dT_kernel<<<1, 1024, 0, st>>>(g, clip, (size_t)Bq * Bv, Tp, dT);
+        const size_t n = (size_t)Bq * Bv;
+        int nb = (int)((n + 16383) / 16384);
+        if (nb > kDtMaxBlocks) nb = kDtMaxBlocks;
+        const size_t per_block = (n + nb - 1) / nb;
+        dT_kernel<<<nb, 1024, 0, st>>>(g, clip, n, per_block, Tp, dT, (double*)((char*)ws + 64), (unsigned int*)((char*)ws + 16));
         TRIAD_LAUNCH_CHECK("dT_kernel");
     }
     return TRIAD_OK;
@@ -956,10 +1008,10 @@ extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, 
         return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_bwd: bad shape");
     if (dtype != TRIAD_DTYPE_F32 && dtype != TRIAD_DTYPE_BF16) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_bwd: dtype");
     if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)dq | (uintptr_t)dv | (uintptr_t)ws) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_bwd: 16-byte alignment");
-    if (!ws || ws_bytes < ((dv || (flags & TRIAD_BWD_PACK_ROWS)) ? triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) : (size_t)256))
+    if (!ws || ws_bytes < ((dv || (flags & TRIAD_BWD_PACK_ROWS)) ? triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) : kCtrlBytes))
         return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    TRIAD_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, st));
+    TRIAD_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, st));      // abort flag + dT ticket
     const bool wide = Nv > 256;
     const size_t pmo = triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) - pack_map_bytes(Bq, Nq);
     if (dtype == TRIAD_DTYPE_BF16) {

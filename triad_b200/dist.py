@@ -51,6 +51,8 @@ class CudaKernels:
         from . import ops
         from . import _lib
         flags = _lib.BWD_PACK_ROWS if (self.packed and q.dtype == torch.bfloat16) else 0
+        if not self.packed:
+            flags |= _lib.BWD_UNIFORM_SCALE
         dq, dv, _ = ops.maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True,
                                     need_dT=False, dv_f32=True, flags=flags)
         return dq, dv
@@ -59,7 +61,9 @@ class CudaKernels:
     # dv / dq separately: lets the sharded step reduce one destination rank's dv while the next one is computed
     def maxmean_bwd_dv(self, q, v, idx, g, scale, T):
         from . import ops
-        _, dv, _ = ops.maxmean_bwd(q, v, idx, g, None, scale, T, need_dq=False, need_dv=True, need_dT=False, dv_f32=True)
+        from . import _lib
+        _, dv, _ = ops.maxmean_bwd(q, v, idx, g, None, scale, T, need_dq=False, need_dv=True, need_dT=False, dv_f32=True,
+                                   flags=0 if self.packed else _lib.BWD_UNIFORM_SCALE)
         return dv
 
     def maxmean_bwd_dq(self, q, v, idx, g, scale, T):
@@ -114,7 +118,10 @@ def sharded_contrastive_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
 
     q_local (Bl,Nq,D), v_local (Bl,Nv,D): this rank's queries and images.  Returns
     {loss (global, fp32 scalar), all_sums [W,8] fp64, clip_rows (Bl,B), dq (Bl,Nq,D), dv (Bl,Nv,D),
-     dT (fp32 scalar)} — gradients of the GLOBAL loss w.r.t. this rank's shards."""
+     dT, dT_global (fp32 scalars)} — dq / dv: gradients of the GLOBAL loss w.r.t. this rank's shards; dT: this
+    rank's SHARE of the global temperature gradient (the shares add up to dT_global), consistent with what
+    back-propagating dq / dv through replicated encoder weights yields on each rank: reduce all of them the
+    same way (SUM, or DDP's mean)."""
     k = kernels if kernels is not None else CudaKernels()
     W = dist.get_world_size(group) if dist.is_initialized() else 1
     r = dist.get_rank(group) if dist.is_initialized() else 0
@@ -158,7 +165,11 @@ def sharded_contrastive_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
         dv32 = _reduce_scatter_rows(dv_partial, W, r, group) if W > 1 else dv_partial
     out["dq"] = dq
     out["dv"] = dv32.to(v_local.dtype)
-    out["dT"] = (all_sums[:, 6].sum() / T.double()).to(torch.float32)
+    # The temperature is REPLICATED across ranks, so — like the gradient of any replicated parameter reached
+    # through dq / dv — each rank returns its own share: sum_{i in this rank's rows, j} g[i,j]*clip[i,j] / T.  A SUM
+    # over ranks (or DDP's mean, which scales every replicated parameter by the same 1/W) gives the global gradient.
+    out["dT"] = (sums[6] / T.double()).to(torch.float32)
+    out["dT_global"] = (all_sums[:, 6].sum() / T.double()).to(torch.float32)
     return out
 
 
@@ -174,7 +185,7 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
                                     both members of its positive pairs — and use the reference's ATen ops;
       temperature calibration       a scalar on T ("av" only).
 
-    Returns {reg, smooth (0.01*l_smooth, "av"), dq (Bl,Nq,D), dv (Bl,Nv,D), dT}."""
+    Returns {reg, smooth (0.01*l_smooth, "av"), dq (Bl,Nq,D), dv (Bl,Nv,D), dT (this rank's share), dT_global}."""
     from . import regularizers as R
     if kind not in ("av", "tv"):
         raise ValueError("kind must be 'av' or 'tv'")
@@ -206,18 +217,20 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
         term = R.patch_sparsity(diag, patch_sparsity_threshold)
         w_term = patch_sparsity_weight
     (term.float() * (w_term / W)).backward()
-    scal = torch.stack([s2.double() / numel, term.detach().double() / W, dT_nn.double(), Tl.grad.double()])
+    # values are global (all-reduced); the temperature gradient stays this rank's SHARE (see sharded_contrastive_step)
+    dT = 0.15 * dT_nn.double() + Tl.grad.double()
+    scal = torch.stack([s2.double() / numel, term.detach().double() / W, dT])
     if W > 1:
         dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
-    l_nonneg, l_term, dT_nonneg, dT_term = scal[0], scal[1], scal[2], scal[3]
+    l_nonneg, l_term, dT_global = scal[0], scal[1], scal[2]
     reg = 0.15 * l_nonneg + w_term * l_term
-    dT = 0.15 * dT_nonneg + dT_term
-    if kind == "av":                                   # 20 * relu(-log T)^2 (model.py:414-424)
+    if kind == "av":                                   # 20 * relu(-log T)^2 (model.py:414-424): a term on T alone
         Td = T.double()
         neg_log = torch.clamp(-torch.log(Td), min=0)
         reg = reg + 20.0 * neg_log ** 2
-        dT = dT - 40.0 * neg_log / Td
-    out = {"reg": reg.to(torch.float32), "dT": dT.to(torch.float32),
+        dT = dT - 40.0 * neg_log / Td / W              # every rank carries 1/W of it, so the shares still add up
+        dT_global = dT_global - 40.0 * neg_log / Td
+    out = {"reg": reg.to(torch.float32), "dT": dT.to(torch.float32), "dT_global": dT_global.to(torch.float32),
            "dq": (0.15 * dq_nn.float() + ql.grad.float()).to(q_local.dtype),
            "dv": (0.15 * dv_nn.float() + vl.grad.float()).to(v_local.dtype)}
     if kind == "av":
@@ -227,7 +240,10 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
 
 class ShardedContrastiveLoss(torch.autograd.Function):
     """Autograd face of sharded_contrastive_step: the forward computes the loss AND the gradients
-    (the saved argmax indices never outlive the call); backward scales them by the incoming grad."""
+    (the saved argmax indices never outlive the call); backward scales them by the incoming grad.
+
+    Every returned gradient — the temperature's included — is this rank's SHARE of the global one: reduce the
+    parameter gradients across ranks with a SUM (or let DDP average all of them alike)."""
 
     @staticmethod
     def forward(ctx, q_local, v_local, temperature, mask_local, group):

@@ -167,7 +167,8 @@ class TriadSimilarityMixin:
         # padded text tokens (weight 0, model.py:509-512) are dropped before the tensor cores
         if attention_mask is not None and q_feats.dtype == torch.bfloat16 and self.triad_pack_masked_rows:
             flags |= _lib_flags.FWD_PACK_ROWS
-        clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale, flags)
+        clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale, flags,
+                                                attention_mask is None)
         handle = TokenSims(q_feats, visual_feats, self.temperature, scale, attention_mask, clip, idx, prefix)
         handle.packed = bool(flags & _lib_flags.FWD_PACK_ROWS)
         handle.fwd_flags = flags

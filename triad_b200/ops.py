@@ -220,13 +220,15 @@ class MaxMeanSimilarity(torch.autograd.Function):
     argmax (src/model.py:387-391 and its autograd backward)."""
 
     @staticmethod
-    def forward(ctx, q, v, temperature, scale, flags):
+    def forward(ctx, q, v, temperature, scale, flags, uniform_scale=False):
         T = temperature_tensor(temperature, q.device)
         clip, idx = maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(q, v, T, scale, idx, clip)
         # rows dropped in the forward (zero weight) have no winners recorded: the backward must skip them too
         ctx.bwd_flags = _lib.BWD_PACK_ROWS if (flags & _lib.FWD_PACK_ROWS) else 0
+        if uniform_scale:                       # no attention mask: every row has weight 1/Nq, the dv sort need not look
+            ctx.bwd_flags |= _lib.BWD_UNIFORM_SCALE
         ctx.mark_non_differentiable(idx)
         ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
         ctx.t_dtype = temperature.dtype if isinstance(temperature, torch.Tensor) else None
@@ -236,12 +238,12 @@ class MaxMeanSimilarity(torch.autograd.Function):
     def backward(ctx, g, _gidx):
         q, v, T, scale, idx, clip = ctx.saved_tensors
         if g is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         need_dq, need_dv, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dq, dv, dT = maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq, need_dv, need_dT, flags=ctx.bwd_flags)
         if dT is not None and ctx.t_shape is not None:
             dT = dT.reshape(ctx.t_shape).to(ctx.t_dtype)
-        return dq, dv, dT, None, None
+        return dq, dv, dT, None, None, None
 
 
 class SymmetricInfoNCE(torch.autograd.Function):
