@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the fused max-mean similarity + symmetric InfoNCE path (fwd + bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl triad|reference] [--config cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl triad|reference] [--config auto|cfg2|cfg3|cfg4]
+                    [--verify] [--no-extras] [--no-cpu-baseline]
 
-metric: clip-pairs/sec = B_global^2 / t(step)   (BASELINE.json).  One "step" = one forward + backward of
-the hot path over one synthetic batch.  N=1 runs BASELINE cfg 2 (B=256, 250 frames x 256 patches, D=512,
-bf16); N>1 (launched by torchrun, one rank per GPU) runs cfg 4 (B=8192 global, rows sharded over the ranks,
-NCCL all-gather / reduce-scatter).  Rank 0 prints ONE JSON line.
+metric: clip-pairs/sec = B_global^2 / t(step)   (BASELINE.json).  One "step" = one forward + backward of the hot path
+over one synthetic batch.  N=1 runs BASELINE cfg 2 (B=256, 250 frames x 256 patches, D=512, bf16); N>1 (launched by
+torchrun, one rank per GPU) runs cfg 4 (B=8192 global, rows sharded over the ranks, NCCL all-gather / reduce).
+Rank 0 prints ONE JSON line.
 
-`value`  : device-resident inputs, CUDA-event timing, max over ranks.
-`e2e`    : the same step through the public drop-in API starting from PINNED HOST buffers (H2D copies of the
-           embeddings and the D2H read of the loss inside the timed region).
-`roofline`: the tcgen05 forward kernel against the measured bf16 peak (MEASURED_PEAKS.json).
-`cpu_baseline`: the oracle's port of the reference's own (materialising) step on this box's host cores.
-`--impl reference`: only that CPU port, as its own JSON line.
+`value`        device-resident inputs, CUDA-event timing, max over ranks.
+`e2e`          the same step through the public drop-in API starting from PINNED HOST buffers (H2D copies of the
+               embeddings and the D2H read of the loss inside the timed region).
+`roofline`     the tcgen05 forward kernel against the measured bf16 peak (MEASURED_PEAKS.json), plus the whole step.
+`cpu_baseline` the reference's own step (oracle/_ref, staged by oracle/build_ref.py; the oracle port if absent) on this
+               box's host cores, bounded sample.
+N=1 extras (each with its own clock sample and roofline): `full_loss`, `cfg3`, `cfg4_rank_shape_1gpu`, `cfg4_1gpu`
+(the B=8192 step on ONE GPU: the strong-scaling denominator of the N>1 lines), `cfg5` (retrieval, HBM-bound).
+N>1 extras: `parity` (the W-rank step vs the single-GPU step on the gathered batch, on the GPUs, before timing)
+and `cfg5_sharded` (gallery sharded by images, local top-k + all-gather merge).
+`--impl reference`: only the CPU arm, as its own JSON line.   `--verify`: only the N-rank parity check.
 """
 from __future__ import annotations
 
@@ -38,9 +44,11 @@ CONFIGS = {
     "cfg4": dict(B=8192, Nq=250, Nv=256, D=512, masked=False,
                  name="cfg4: B=8192 global, 250 x 256, D=512, bf16 fwd+bwd, rows sharded over ranks"),
 }
+CFG5 = dict(n_img=100000, Nv=1024, D=512, k=10,
+            name="cfg5: 1 query x 100 000 gallery images x 1024 patches, D=512, bf16, forward-only top-10")
 
 
-def algorithmic_flops(B_rows, B_cols, n_tokens_total, Nv, D):
+def algorithmic_flops(B_cols, n_tokens_total, Nv, D):
     """2*Bcols*(sum n_i)*Nv*D forward + 4*Bcols*(sum n_i)*D sparse backward."""
     return 2.0 * B_cols * n_tokens_total * Nv * D, 4.0 * B_cols * n_tokens_total * D
 
@@ -49,12 +57,13 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
-    return 1590.0, 1400.0, "fallback"
+        return {"bf16": float(d["bf16_tflops"]), "bf16_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                "hbm": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16": 1590.0, "bf16_sustained": 1400.0, "hbm": 6500.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during a timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -65,10 +74,11 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.08)                    # the first sample is out before the timed region starts
         except Exception:
             self.proc = None
         return self
@@ -79,7 +89,7 @@ class ClockSampler:
 
     def __exit__(self, *a):
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -87,11 +97,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, pw, reasons = [], 0.0, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                sm.append(float(r[0])); mx = max(mx, float(r[1])); pw.append(float(r[2]))
                 for n, val in zip(names, r[3:7]):
                     if val.lower().startswith("active"):
                         reasons.add(n)
@@ -99,33 +109,56 @@ class ClockSampler:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        hi = sorted(sm)[len(sm) // 2:]            # the samples under load are the upper half when the region is short
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "sm_mhz_upper_half_median": statistics.median(hi)}
+                "sm_mhz_min": min(sm), "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's port of the reference step (materialises token_sims, autograd)
+# CPU arm: the reference's own step on the host cores
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_factory(cfg, B_sample):
+    """Returns (step, kind, what).  kind "reference": the unmodified reference methods from oracle/_ref (staged by
+    oracle/build_ref.py): compute_all_similarities_{av,tv} + compute_contrastive_loss_{av,tv} with the regularisers
+    bound to zero, i.e. the reference's own similarity / max-mean / statistics / InfoNCE lines and autograd backward —
+    the like-for-like of the metric.  kind "port": the oracle's restatement of the same lines, when oracle/_ref is
+    not there."""
     import torch
     from oracle import oracle as O
+    from oracle import ref_loader
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     q, v, mask = O.make_inputs(B_sample, cfg["Nq"], cfg["Nv"], cfg["D"], torch.float32, seed=1234,
                                masked=cfg["masked"], min_len=8)
-    T = torch.tensor(1.5, requires_grad=True)
     q.requires_grad_(True)
     v.requires_grad_(True)
+    ref = ref_loader.load()
+    if ref is not None:
+        M = ref[0].MultiModalModel
+        stub = ref_loader.make_stub(M, 1.5, regularizers=False)
 
-    def step():
+        def step():
+            q.grad = v.grad = stub.temperature.grad = None
+            if mask is None:
+                clip, tok = M.compute_all_similarities_av(stub, q, v)
+                total = M.compute_contrastive_loss_av(stub, clip, tok)[0]
+            else:
+                clip, tok = M.compute_all_similarities_tv(stub, q, v, mask)
+                total = M.compute_contrastive_loss_tv(stub, clip, tok)[0]
+            total.backward()
+            return float(total)
+        return step, "reference", ("the reference's own methods, unmodified (oracle/_ref/model.py: compute_all_similarities_* + "
+                                   "compute_contrastive_loss_* with zero regularisers), fp32, autograd backward")
+    T = torch.tensor(1.5, requires_grad=True)
+
+    def step_port():
         q.grad = v.grad = T.grad = None
         loss, _, _ = O.reference_step_autograd(q, v, T, mask)
         return float(loss)
-    return step
+    return step_port, "port", "oracle.reference_step_autograd (restatement of the reference's materialising fwd+bwd), fp32"
 
 
 def cpu_baseline(cfg, budget_s=12.0, B_sample=32):
-    step = cpu_reference_step_factory(cfg, B_sample)
+    import torch
+    step, kind, what = cpu_reference_step_factory(cfg, B_sample)
     step()                                   # warm-up
     t0, n = time.perf_counter(), 0
     while True:
@@ -133,24 +166,21 @@ def cpu_baseline(cfg, budget_s=12.0, B_sample=32):
         el = time.perf_counter() - t0
         if el >= budget_s or n >= 50:
             break
-    import torch
     return {"value": B_sample * B_sample * n / el, "unit": "clip-pairs/s", "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": f"oracle.reference_step_autograd (the reference's materialising fwd+bwd, fp32) on a "
-                      f"B={B_sample} sub-batch of the same shape (Nq={cfg['Nq']}, Nv={cfg['Nv']}, D={cfg['D']}), "
-                      f"{n} steps in {el:.1f} s; pairs/s is per-pair work, so it transfers to the full batch"}
+            "kind": kind,
+            "sample": f"{what}, on a B={B_sample} sub-batch of the same shape (Nq={cfg['Nq']}, Nv={cfg['Nv']}, "
+                      f"D={cfg['D']}), {n} steps in {el:.1f} s; pairs/s is per-pair work, so it transfers to the full batch"}
 
 
 def run_reference(args, cfg_key):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
-    Python and does not travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     cfg = CONFIGS[cfg_key]
     Bs = 32
-    step = cpu_reference_step_factory(cfg, Bs)
+    step, kind, what = cpu_reference_step_factory(cfg, Bs)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -159,14 +189,13 @@ def run_reference(args, cfg_key):
     el = time.perf_counter() - t0
     val = Bs * Bs * args.steps / el
     cores = torch.get_num_threads()
-    sample = (f"each step = fwd+bwd of the reference's materialising path (oracle port, fp32) on a B={Bs} sub-batch "
-              f"of {cfg['name']}")
+    sample = f"each step = fwd+bwd of {what} on a B={Bs} sub-batch of {cfg['name']}"
     print(json.dumps({
         "impl": "reference", "metric": "clip-pairs/sec", "value": val, "unit": "clip-pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "sample_batch": Bs},
-        "cpu_baseline": {"value": val, "unit": "clip-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "clip-pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "clip-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
@@ -191,6 +220,67 @@ def make_device_inputs(cfg, B_local, seed, device, n_sets):
     return sets
 
 
+def rel_err(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def verify_sharded(world, rank, dev, group=None):
+    """N-rank parity on the GPUs (NCCL): sharded_contrastive_step on W shards vs the single-GPU drop-in on the gathered
+    batch (every rank recomputes it), unmasked and masked; and, at a small size, vs the CPU oracle on rank 0.
+    Returns a dict; raises AssertionError on a mismatch."""
+    import torch
+    import torch.distributed as dist
+    import triad_b200
+    from triad_b200.dist import sharded_contrastive_step
+    out = {"parity_nranks": world}
+    worst = {"loss": 0.0, "dq": 0.0, "dv": 0.0, "dT": 0.0, "clip": 0.0}
+    for masked, (Bl, Nq, Nv, D) in ((False, (64, 250, 256, 512)), (True, (48, 77, 256, 512)), (False, (8, 50, 256, 512))):
+        B = Bl * world
+        cfg = dict(Nq=Nq, Nv=Nv, D=D, masked=masked)
+        (q, v, mask), = make_device_inputs(cfg, B, 4242 + Nq, dev, 1)          # same seed on every rank: same full batch
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        T = torch.tensor(1.5, device=dev)
+        sh = sharded_contrastive_step(q[sl].contiguous(), v[sl].contiguous(), T, None if mask is None else mask[sl].contiguous(),
+                                      group=group)
+        m = triad_b200.TriadHotPath(temperature=1.5).to(dev)
+        m.triad_regularizers = False
+        qd, vd = q.clone().requires_grad_(True), v.clone().requires_grad_(True)
+        if mask is None:
+            clip, tok = m.compute_all_similarities_av(qd, vd)
+            con = m.compute_contrastive_loss_av(clip, tok)[1]
+        else:
+            clip, tok = m.compute_all_similarities_tv(qd, vd, mask)
+            con = m.compute_contrastive_loss_tv(clip, tok)[0]
+        con.backward()
+        dT_sum = sh["dT"].clone()
+        if world > 1:
+            dist.all_reduce(dT_sum, op=dist.ReduceOp.SUM, group=group)
+        errs = {"loss": abs(sh["loss"].item() - con.item()) / abs(con.item()),
+                "clip": rel_err(sh["clip_rows"], tok.clip.detach()[sl]),
+                "dq": rel_err(sh["dq"], qd.grad[sl]), "dv": rel_err(sh["dv"], vd.grad[sl]),
+                "dT": abs(dT_sum.item() - m.temperature.grad.item()) / max(abs(m.temperature.grad.item()), 1e-12),
+                "dT_global": abs(sh["dT_global"].item() - m.temperature.grad.item()) / max(abs(m.temperature.grad.item()), 1e-12)}
+        # same kernels, same winners: clip rows agree to the fp32 summation order of the per-group partial sums (the
+        # 32-row groups start at the shard's first row); g then differs only by that and by the order in which the
+        # column partials are combined, so dq / dv agree to well below one bf16 rounding
+        assert errs["clip"] < 2e-6, (masked, errs)
+        assert errs["loss"] < 1e-6 and errs["dq"] < 2e-3 and errs["dv"] < 2e-3, (masked, errs)
+        assert errs["dT"] < 1e-3 and errs["dT_global"] < 1e-3, (masked, errs)
+        for k in worst:
+            worst[k] = max(worst[k], errs[k])
+        if Bl == 8 and rank == 0:               # and the oracle, where it finishes in seconds
+            from oracle import oracle as O
+            ref = O.contrastive_step_closed_form(q.cpu(), v.cpu(), 1.5, None)
+            e = {"loss": abs(sh["loss"].item() - ref["loss"].item()) / abs(ref["loss"].item()),
+                 "dq": rel_err(sh["dq"].cpu(), ref["dq"][sl]), "dv": rel_err(sh["dv"].cpu(), ref["dv"][sl])}
+            assert e["loss"] < 1e-5 and e["dq"] < 1e-2 and e["dv"] < 1e-2, e
+            out["vs_oracle"] = e
+    out["parity"] = "ok"
+    out["worst_rel_err_vs_single_gpu"] = worst
+    return out
+
+
 def run_triad(args, cfg_key):
     import torch
     import torch.distributed as dist
@@ -207,6 +297,38 @@ def run_triad(args, cfg_key):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     _lib.check(lib.triad_device_check(local), "triad_device_check")
+    peaks = measured_peaks()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, K):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # ---- N-rank parity on the GPUs, before anything is timed -------------------------------------
+    parity = None
+    if world > 1 or args.verify:
+        parity = verify_sharded(world, rank, dev)
+        if args.verify:
+            if rank == 0:
+                print(json.dumps(parity), flush=True)
+            if world > 1:
+                dist.barrier()
+                dist.destroy_process_group()
+            return parity
 
     cfg = CONFIGS[cfg_key]
     B = cfg["B"]
@@ -218,26 +340,26 @@ def run_triad(args, cfg_key):
     model = triad_b200.TriadHotPath(temperature=1.5).to(dev)
     model.triad_regularizers = False       # BASELINE.json's metric: max-mean similarity + InfoNCE, fwd + bwd
     T = model.temperature
-    tokens_local = int(sets[0][2].sum().item()) if cfg["masked"] else Bl * cfg["Nq"]
     fwd_ev = []
 
-    def step_single(q, v, mask, record=False):
-        q.grad = v.grad = T.grad = None
+    def api_step(m, q, v, mask, record=False):
+        """One step through the drop-in methods (the calls forward_audio_visual / forward_text_visual make)."""
+        q.grad = v.grad = m.temperature.grad = None
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if mask is None:
-            clip, tok = model.compute_all_similarities_av(q, v)
+            clip, tok = m.compute_all_similarities_av(q, v)
         else:
-            clip, tok = model.compute_all_similarities_tv(q, v, mask)
+            clip, tok = m.compute_all_similarities_tv(q, v, mask)
         if record:
             e1.record(); fwd_ev.append((e0, e1))
-        if mask is None:
-            total, con, reg, smooth, stats = model.compute_contrastive_loss_av(clip, tok)
-        else:
-            total, stats = model.compute_contrastive_loss_tv(clip, tok)
+        total = m.compute_contrastive_loss_av(clip, tok)[0] if mask is None else m.compute_contrastive_loss_tv(clip, tok)[0]
         total.backward()
         return total
+
+    def step_single(q, v, mask, record=False):
+        return api_step(model, q, v, mask, record)
 
     class TimedKernels(CudaKernels):
         """The product kernels, with CUDA events around the forward call (for the roofline entry)."""
@@ -262,25 +384,6 @@ def run_triad(args, cfg_key):
     step = step_single if world == 1 else step_sharded
     for s in sets:
         s[0].requires_grad_(world == 1); s[1].requires_grad_(world == 1)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, K):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(K):
-            fn(i)
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
 
     # ---- device-resident arm -------------------------------------------------------------------
     for i in range(args.warmup):
@@ -360,77 +463,136 @@ def run_triad(args, cfg_key):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = e2e_t.item()
     h2d = in_bytes + (host[0][2].numel() * 8 if host[0][2] is not None else 0)
+    del host, staged
+    tokens_local = int(sets[0][2].sum().item()) if cfg["masked"] else Bl * cfg["Nq"]
 
-    # ---- the reference's FULL loss (contrastive + regularisers), reported beside the metric ----
-    full = None
-    if world == 1:
+    # ---- roofline of the dominant kernel (tcgen05 forward) and of the step ------------------------------------
+    def roofline_block(fwd_ms, step_ms, Bcols, tokens, Nv, D, nranks=1, traffic=None):
+        f_fwd, f_bwd = algorithmic_flops(Bcols, tokens, Nv, D)
+        achieved = f_fwd / (fwd_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": "maxmean_tc_kernel (fwd call: memset + kernel + finalize_clip)",
+                "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
+                "peak_source": f"{peaks['source']}: burst; sustained {peaks['bf16_sustained']}",
+                "frac_of_sustained": achieved / peaks["bf16_sustained"], "ms": fwd_ms, "traffic": traffic,
+                "algorithmic_flops_per_launch": f_fwd, "step_flops": f_fwd + f_bwd,
+                "step_frac_of_peak": (f_fwd + f_bwd) / (step_ms * 1e-3) / 1e12 / peaks["bf16"]}
+
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(cfg_key)
+    roof = None
+    if fwd_ev:
+        fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+        roof = roofline_block(fwd_ms, ms, B, tokens_local, cfg["Nv"], cfg["D"], world, traffic)
+    fwd_ev.clear()
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        # ---- the reference's FULL loss (contrastive + regularisers), reported beside the metric ----
         model.triad_regularizers = True
         for i in range(2):
             step(*sets[i % n_sets])
         k_full = max(3, min(args.steps, 10))
-        full_ms = timed(lambda i: step(*sets[i % n_sets]), k_full)
+        with ClockSampler(local) as ck:
+            full_ms = timed(lambda i: step(*sets[i % n_sets]), k_full)
         model.triad_regularizers = False
-        full = {"value": float(B) * B / (full_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": full_ms, "steps": k_full,
-                "what": "same step with the reference's regularisers on (model.py:394-428 / :516-542): dense non-negative "
-                        "pressure (tcgen05 forward in dense-regulariser mode + 2 library GEMMs per image chunk), smoothness / "
-                        "sparsity on the positive pairs; not part of BASELINE.json's metric"}
+        extras["full_loss"] = {
+            "value": float(B) * B / (full_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": full_ms, "steps": k_full,
+            "clocks": ck.summary(),
+            "what": "same step with the reference's regularisers on (model.py:394-428 / :516-542): dense non-negative "
+                    "pressure, smoothness / sparsity on the positive pairs; not part of BASELINE.json's metric"}
+        del sets
+        torch.cuda.empty_cache()
 
-    # ---- single-GPU rate at the multi-GPU workload's per-rank shape (the strong-scaling denominator) ----------
-    # N > 1 runs cfg 4 (B = 8192); one GPU's share of that at 8 ranks is 1024 queries x 8192 images.  Timing that
-    # shape here gives the per-GPU rate the N-GPU numbers should be compared with (cfg 2's B = 256 step is short
-    # enough to run at boost clocks; 0.8 s of continuous tensor work runs under the power cap).
-    rank_shape = None
-    if world == 1 and cfg_key == "cfg2" and not args.no_rank_shape:
+        # ---- cfg 3: ragged text queries (masked mean), B=512 ----------------------------------------------------
+        if cfg_key != "cfg3":
+            c3 = CONFIGS["cfg3"]
+            s3 = make_device_inputs(c3, c3["B"], 777, dev, 3)
+            for s in s3:
+                s[0].requires_grad_(True); s[1].requires_grad_(True)
+            for i in range(3):
+                step_single(*s3[i % 3])
+            fwd_ev.clear()
+            k3 = max(5, min(args.steps, 20))
+            with ClockSampler(local) as ck:
+                ms3 = timed(lambda i: step_single(*s3[i % 3], record=True), k3)
+            tok3 = float(sum(int(s[2].sum().item()) for s in s3)) / 3.0
+            fwd3 = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+            fwd_ev.clear()
+            extras["cfg3"] = {"workload": c3["name"], "ms_per_step": ms3, "steps": k3,
+                              "value": float(c3["B"]) ** 2 / (ms3 * 1e-3), "unit": "clip-pairs/s", "clocks": ck.summary(),
+                              "valid_tokens_per_step": tok3,
+                              "roofline": roofline_block(fwd3, ms3, c3["B"], tok3, c3["Nv"], c3["D"], 1,
+                                                         json.load(open(tpath)).get("cfg3") if os.path.exists(tpath) else None),
+                              "note": "flops count VALID tokens only (padded tokens are packed out before the tensor cores)"}
+            del s3
+            torch.cuda.empty_cache()
+
+        # ---- cfg 4: one rank's share (1024 x 8192), then the whole B=8192 step, on ONE GPU ------------------------
         c4 = CONFIGS["cfg4"]
         Bq4, Bv4 = c4["B"] // 8, c4["B"]
-        (q4, _, _), = make_device_inputs(c4, Bq4, 99, dev, 1)
+        (q4, _, _), = make_device_inputs(c4, Bv4, 99, dev, 1)
         (_, v4, _), = make_device_inputs(c4, Bv4, 98, dev, 1)
         T4 = torch.tensor(1.5, device=dev)
-        ck = CudaKernels()
+        ck4 = CudaKernels()
+        q4r = q4[:Bq4].contiguous()
 
         def rank_step():
-            sc = ck.row_scale(None, Bq4, c4["Nq"], dev)
-            clip4, idx4 = ck.maxmean_fwd(q4, v4, sc, T4)
-            lse4, cp4 = ck.infonce_partial(clip4, Bv4, 0)
-            g4, _ = ck.infonce_finish(clip4, Bv4, 0, lse4, cp4.reshape(1, 2, Bv4))
-            return ck.maxmean_bwd(q4, v4, idx4, g4, clip4, sc, T4)
+            sc = ck4.row_scale(None, Bq4, c4["Nq"], dev)
+            clip4, idx4 = ck4.maxmean_fwd(q4r, v4, sc, T4)
+            lse4, cp4 = ck4.infonce_partial(clip4, Bv4, 0)
+            g4, _ = ck4.infonce_finish(clip4, Bv4, 0, lse4, cp4.reshape(1, 2, Bv4))
+            return ck4.maxmean_bwd(q4r, v4, idx4, g4, clip4, sc, T4)
 
         rank_step()
-        rs_ms = timed(lambda i: rank_step(), 2)
-        rank_shape = {"workload": f"one rank's share of cfg4 at 8 GPUs: {Bq4} queries x {Bv4} images, fwd + InfoNCE block + bwd, "
-                                  "no collectives", "ms_per_step": rs_ms, "value": float(Bq4) * Bv4 / (rs_ms * 1e-3),
-                      "unit": "clip-pairs/s per GPU"}
+        with ClockSampler(local) as ck:
+            rs_ms = timed(lambda i: rank_step(), 2)
+        extras["cfg4_rank_shape_1gpu"] = {
+            "workload": f"one rank's share of cfg4 at 8 GPUs: {Bq4} queries x {Bv4} images, fwd + InfoNCE block + bwd, no collectives",
+            "ms_per_step": rs_ms, "value": float(Bq4) * Bv4 / (rs_ms * 1e-3), "unit": "clip-pairs/s per GPU", "clocks": ck.summary()}
+        del q4r
+        if not args.no_cfg4_1gpu:
+            m4 = triad_b200.TriadHotPath(temperature=1.5).to(dev)
+            m4.triad_regularizers = False
+            q4.requires_grad_(True); v4.requires_grad_(True)
+            api_step(m4, q4, v4, None)                       # warm-up (allocates the 17 GB argmax buffer once)
+            fwd_ev.clear()
+            with ClockSampler(local) as ck:
+                ms4 = timed(lambda i: api_step(m4, q4, v4, None, record=True), 2)
+            fwd4 = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+            fwd_ev.clear()
+            extras["cfg4_1gpu"] = {
+                "workload": "cfg4 on ONE GPU: B=8192 x 8192, 250 x 256, D=512, bf16, fwd + InfoNCE + bwd through the drop-in API "
+                            "(the strong-scaling denominator of the N>1 lines)",
+                "ms_per_step": ms4, "steps": 2, "value": float(c4["B"]) ** 2 / (ms4 * 1e-3), "unit": "clip-pairs/s",
+                "clocks": ck.summary(),
+                "roofline": roofline_block(fwd4, ms4, c4["B"], c4["B"] * c4["Nq"], c4["Nv"], c4["D"])}
+            q4.grad = v4.grad = None
+            del m4
         del q4, v4
         torch.cuda.empty_cache()
 
-    # ---- roofline of the dominant kernel (tcgen05 forward) ---------------------------------------
-    peak, peak_sustained, peak_src = measured_peaks()
-    roof = None
-    if fwd_ev:
-        fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
-        f_fwd, f_bwd = algorithmic_flops(Bl, B, tokens_local, cfg["Nv"], cfg["D"])
-        achieved = f_fwd / (fwd_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(cfg_key)
-        roof = {"bound": "tensor", "kernel": "maxmean_tc_kernel (fwd call: memset + kernel + finalize_clip)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": f"{peak_src} (burst); sustained {peak_sustained}",
-                "frac_of_sustained": achieved / peak_sustained, "ms": fwd_ms, "traffic": traffic,
-                "step_flops": f_fwd + f_bwd,
-                "step_frac_of_peak": (f_fwd + f_bwd) * world / (ms * 1e-3) / 1e12 / (peak * world)}
+        # ---- cfg 5: one query against a 104.9 GB gallery, forward-only top-k (HBM-bound for text queries) ---------
+        if not args.no_cfg5:
+            extras["cfg5"] = cfg5_block(dev, local, peaks, 1, 0, timed)
+
+    if world > 1 and not args.no_extras and not args.no_cfg5:
+        extras["cfg5_sharded"] = cfg5_block(dev, local, peaks, world, rank, timed)
 
     out = None
     if rank == 0:
         out = {
             "metric": "clip-pairs/sec", "value": value, "unit": "clip-pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["name"], "global_batch": B, "rows_per_rank": Bl,
                        "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                        "l2": f"{n_sets} rotating input sets ({n_sets * in_bytes / 2**20:.0f} MiB) > 126 MB L2, "
-                             "so every step reads its embeddings from HBM"},
+                             "so every step reads its embeddings from HBM",
+                       "scaling_note": "N=1 runs cfg 2 (the configuration the metric is quoted on); N>1 runs cfg 4 with the TOTAL "
+                                       "work fixed (B=8192), i.e. strong scaling among the N>1 lines; the same B=8192 step on one "
+                                       "GPU is the `cfg4_1gpu` block of the N=1 line"},
             "clocks": clocks.summary(),
             "e2e": {"value": float(B) * B / (e2e_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h["bytes"],
@@ -439,10 +601,9 @@ def run_triad(args, cfg_key):
             "gpu_launches": gpu_launches,
             "roofline": roof,
         }
-        if full is not None:
-            out["full_loss"] = full
-        if rank_shape is not None:
-            out["cfg4_rank_shape_1gpu"] = rank_shape
+        if parity is not None:
+            out.update({"parity_nranks": parity["parity_nranks"], "parity": parity["parity"], "parity_detail": parity})
+        out.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_seconds)
         print(json.dumps(out), flush=True)
@@ -452,15 +613,66 @@ def run_triad(args, cfg_key):
     return out
 
 
+def cfg5_block(dev, local, peaks, world, rank, timed):
+    """cfg 5: one query (77 text tokens / 250 audio frames) against 100 000 images x 1024 patches (104.9 GB bf16).
+    world == 1: the whole gallery on this GPU.  world > 1: the gallery sharded by images over the ranks, local top-k,
+    all-gather of k (score, id) pairs, merge (triad_b200.dist.sharded_retrieve_topk)."""
+    import torch
+    from triad_b200 import retrieval as R
+    n_img, Nv, D, k = CFG5["n_img"], CFG5["Nv"], CFG5["D"], CFG5["k"]
+    n_loc = n_img // world + (1 if rank < n_img % world else 0)
+    id0 = rank * (n_img // world) + min(rank, n_img % world)
+    gal = torch.empty(n_loc, Nv, D, dtype=torch.bfloat16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    step_imgs = max(1, (1 << 30) // (Nv * D * 2))                       # fill 1 GiB at a time
+    for i in range(0, n_loc, step_imgs):
+        blk = torch.randn(min(step_imgs, n_loc - i), Nv, D, generator=g, device=dev, dtype=torch.float32)
+        gal[i:i + blk.shape[0]] = torch.nn.functional.normalize(blk, dim=2).to(torch.bfloat16)
+        del blk
+    gq = torch.Generator(device=dev).manual_seed(11)                    # the same query on every rank
+    res = {"workload": CFG5["name"] + (f", gallery sharded over {world} ranks" if world > 1 else ""),
+           "gallery_bytes": float(n_img) * Nv * D * 2, "queries": {}}
+    for name, Nq in (("text77", 77), ("audio250", 250)):
+        q = torch.nn.functional.normalize(torch.randn(Nq, D, generator=gq, device=dev), dim=1).to(torch.bfloat16)
+        if world > 1:
+            from triad_b200.dist import sharded_retrieve_topk
+            fn = lambda i: sharded_retrieve_topk(q, gal, 1.5, k, id0)           # noqa: E731
+        else:
+            fn = lambda i: R.retrieve_topk(q, gal, 1.5, k)                       # noqa: E731
+        s, ids = fn(0)
+        with ClockSampler(local) as ck:
+            ms = timed(fn, 5)
+        # spot check of the winner against a plain fp32 evaluation (on the rank that owns it)
+        j = int(ids[0]) - id0
+        chk = None
+        if 0 <= j < n_loc:
+            ref = ((q.float() @ gal[j].float().t()) / 1.5).max(dim=1).values.mean().item()
+            chk = abs(ref - s[0].item())
+        gbs = res["gallery_bytes"] / (ms * 1e-3) / 1e9
+        flops = 2.0 * Nq * n_img * Nv * D
+        bound = "hbm" if Nq < peaks["bf16"] * 1e3 / peaks["hbm"] else "tensor/hbm (balanced)"
+        res["queries"][name] = {
+            "Nq": Nq, "ms_per_query": ms, "queries_per_s": 1e3 / ms, "clocks": ck.summary(), "top1_fp32_check_abs_err": chk,
+            "roofline": {"bound": bound, "achieved": gbs, "peak": peaks["hbm"] * world, "unit": "GB/s",
+                         "frac": gbs / (peaks["hbm"] * world), "algorithmic_bytes_per_launch": res["gallery_bytes"],
+                         "tflops": flops / (ms * 1e-3) / 1e12, "peak_source": peaks["source"]}}
+    del gal
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="triad", choices=["triad", "reference"])
     ap.add_argument("--config", default="auto", choices=["auto"] + list(CONFIGS))
+    ap.add_argument("--verify", action="store_true", help="only the N-rank parity check (sharded vs single-GPU vs oracle)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-rank-shape", action="store_true", help="skip the cfg4 per-rank-shape timing at N=1")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 / cfg5 / full-loss blocks")
+    ap.add_argument("--no-cfg4-1gpu", action="store_true", help="skip the B=8192 single-GPU step (about 20 s)")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the 104.9 GB retrieval block")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -57,6 +57,9 @@ extern "C" {
 #define TRIAD_FWD_PACK_ROWS   16   /* bf16 tensor-core path: rows whose row_scale is 0 (padded text tokens,
                                       model.py:509-512) are dropped before the GEMM; their idx entries read 0 */
 
+#define TRIAD_FWD_TEST_TRIP_WATCHDOG 32 /* test aid: raise the pipeline-watchdog flag after the kernel, as a timed-out
+                                         barrier wait would: clip must come back NaN (never a silent garbage matrix) */
+
 int         triad_abi_version(void);
 const char* triad_status_string(int status);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
@@ -148,6 +151,7 @@ int triad_contrastive_head(const float* clip, int B, const float* temperature,
                                       get an exact zero gradient without being gathered for)                */
 #define TRIAD_BWD_UNIFORM_SCALE 128  /* the caller guarantees row_scale has no zeros (no attention mask): the dv sort then
                                       does not read it per row to decide which rows to list                            */
+#define TRIAD_BWD_TEST_TRIP_WATCHDOG 256 /* test aid: raise the watchdog flag before the kernels run: dq must come back NaN */
 #define TRIAD_BWD_DQ_STAGED    64   /* dq: the round-1 kernel (winners/weights staged through shared memory) — cross-check */
 size_t triad_maxmean_bwd_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D, int dtype);
 int triad_maxmean_bwd(const void* q, const void* v, const void* idx, const float* g,

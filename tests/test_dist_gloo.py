@@ -129,3 +129,59 @@ def test_two_rank_regularisers_match_full_batch(kind):
         if kind == "av":
             assert abs(o["smooth"] - smooth.item()) < 1e-5 * abs(smooth.item())
     assert abs(sum(ret[r]["dT"] for r in range(world)) - T64.grad.item()) < 1e-4 * abs(T64.grad.item())
+
+
+# ---- gallery-sharded retrieval (cfg 5): local top-k + all-gather + merge ------------------------------
+def _oracle_topk(q, gallery, temperature, k, direction):
+    """CPU stand-in of triad_b200.retrieval.retrieve_topk: scores with the oracle's aggregator (retrieval.py:106-115),
+    top-k in the library's order (score descending, ties to the lower id)."""
+    s = torch.tensor([O.aggregate_pair(q, gallery[n], temperature, "q2v" if direction == 0 else "v2q")
+                      for n in range(gallery.shape[0])], dtype=torch.float32)
+    order = torch.argsort(s, descending=True, stable=True)[:k]
+    return s[order], order.to(torch.int32)
+
+
+def _gallery(n_img, Nq, Nv, D):
+    g = torch.Generator().manual_seed(21)
+    q = torch.nn.functional.normalize(torch.randn(Nq, D, generator=g), dim=1)
+    gal = torch.nn.functional.normalize(torch.randn(n_img, Nv, D, generator=g), dim=2)
+    if n_img > 9:
+        gal[9] = gal[2]                  # exact ties across (and inside) shards: the lower id must win
+        gal[5] = gal[2]
+    else:
+        gal[n_img - 1] = gal[0]
+    return q, gal
+
+
+def _retrieve_worker(rank, world, port, n_img, k, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from triad_b200.dist import sharded_retrieve_topk
+        q, gal = _gallery(n_img, 6, 10, 16)
+        base, rem = n_img // world, n_img % world            # uneven shards
+        n_loc = base + (1 if rank < rem else 0)
+        id0 = rank * base + min(rank, rem)
+        s, ids = sharded_retrieve_topk(q, gal[id0:id0 + n_loc], 1.5, k, id0, local_topk=_oracle_topk)
+        ret[rank] = (s, ids)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_img,k", [(11, 4), (3, 5)])
+def test_two_rank_sharded_retrieval_matches_single_gallery(n_img, k):
+    """ids bit-equal to the top-k over the whole gallery, on every rank; k larger than a shard (and than the gallery)
+    pads with -inf candidates that never win over real ones."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_retrieve_worker, args=(world, _free_port(), n_img, k, ret), nprocs=world, join=True)
+    q, gal = _gallery(n_img, 6, 10, 16)
+    want_s, want_i = _oracle_topk(q, gal, 1.5, min(k, n_img), 0)
+    for r in range(world):
+        s, ids = ret[r]
+        n = min(k, n_img)
+        assert torch.equal(ids[:n], want_i.to(torch.int64)), (ids, want_i)
+        assert torch.equal(s[:n], want_s)
+        assert bool(torch.isinf(s[n:]).all())

@@ -9,5 +9,6 @@ pytestmark = pytest.mark.gpu
 def test_random_shapes_match_oracle(seed):
     from tools import fuzz_gpu
     worst, failures = fuzz_gpu.run_cases(30, seed, verbose=False)
+    print({"fuzz_seed": seed, "idx_mismatch_total": worst["idx_mismatch_total"], "idx_rows_total": worst["idx_rows_total"]})
     assert not failures, failures
     assert worst["dq"] < 6e-3 and worst["dv"] < 6e-3

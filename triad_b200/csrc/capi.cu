@@ -117,7 +117,8 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
         rc = launch_maxmean_tc(qp, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags,
                                (const int*)maps, nullptr, st);
         if (rc) return rc;
-        return launch_finalize_clip_packed(part, (const int*)maps, Bq, Bv, Nq, clip, st);
+        if (flags & TRIAD_FWD_TEST_TRIP_WATCHDOG) TRIAD_CUDA_CHECK(cudaMemsetAsync(abort_flag, 1, 4, st));
+        return launch_finalize_clip_packed(part, (const int*)maps, Bq, Bv, Nq, clip, abort_flag, st);
     }
     if (use_tc) {
         // A single row tile of <= 128 tokens (one text query against a gallery): cta_group::1 — a pair would
@@ -129,7 +130,8 @@ static int fwd_impl(const void* q, const void* v, const float* row_scale, const 
         rc = launch_maxmean_simt(q, v, row_scale, temperature, inv_T, M, Bv, Nq, Nv, D, dtype, part, idx, st);
     }
     if (rc) return rc;
-    return launch_finalize_clip(part, Bq, Bv, Nq, clip, st);
+    if (flags & TRIAD_FWD_TEST_TRIP_WATCHDOG) TRIAD_CUDA_CHECK(cudaMemsetAsync(abort_flag, 1, 4, st));
+    return launch_finalize_clip(part, Bq, Bv, Nq, clip, abort_flag, st);
 }
 
 extern "C" int triad_maxmean_fwd(const void* q, const void* v, const float* row_scale, const float* temperature,

@@ -93,12 +93,14 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
                       float* part, void* idx, int* abort_flag, int cta_group, int flags, const int* pack_maps,
                       const EmitNArgs* emit, cudaStream_t st);
-int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
+int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, const int* abort_flag, cudaStream_t st);
 // packed rows (pack.cu): maps = off[Bq+1] | rowmap[Bq*Nq] | scratch
 size_t pack_map_bytes(int Bq, int Nq);
 int launch_pack_map(const float* row_scale, int Bq, int Nq, void* maps, cudaStream_t st);
+int launch_pack_groups(const float* row_scale, int Bq, int Nq, void* maps, cudaStream_t st);   // goff[Bq+1] | glist | cnt
 int launch_pack_copy(const void* q, const void* maps, int Bq, int Nq, int D, int elt_bytes, void* qp, cudaStream_t st);
-int launch_finalize_clip_packed(const float* part, const int* pack_off, int Bq, int Bv, int Nq, float* clip, cudaStream_t st);
+int launch_finalize_clip_packed(const float* part, const int* pack_off, int Bq, int Bv, int Nq, float* clip,
+                                const int* abort_flag, cudaStream_t st);
 // partial sums of the packed forward: part[(j*Bq + i)*pieces + piece], piece = (32-row group of the packed row)
 // - (group of the query's first packed row); a query of <= Nq kept rows spans at most (Nq+30)/32 + 1 groups
 static inline int packed_pieces(int Nq) { return (Nq + 30) / 32 + 1; }

@@ -36,12 +36,12 @@ static inline NceWs nce_ws_carve(void* ws, int rows, int B) {
 
 // ---- step 1a: one CTA = 32 rows; warps reduce rows, then threads own columns ---------------
 __global__ void __launch_bounds__(kNceThreads)
-nce_partial_kernel(const float* __restrict__ clip, int rows, int B,
+nce_partial_kernel(const float* __restrict__ clip, int rows, int B, int rpb,
                    float* __restrict__ row_lse, float* __restrict__ chunk_part, unsigned int* __restrict__ ticket) {
     if (ticket && blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;     // the fused head's "last block" ticket
     const int blk = blockIdx.x;
-    const int r0 = blk * kNceRowsPerBlock;
-    const int nr = min(kNceRowsPerBlock, rows - r0);
+    const int r0 = blk * rpb;
+    const int nr = min(rpb, rows - r0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // row log-sum-exp: 8 warps x 4 rows each, two shuffle reductions per row
@@ -158,7 +158,7 @@ __global__ void nce_final_reduce_kernel(const double* __restrict__ blk_sums, int
 constexpr int kHeadMaxBlocks = 64;
 
 __global__ void __launch_bounds__(kNceThreads)
-nce_head_kernel(const float* __restrict__ clip, int B, const float* __restrict__ row_lse,
+nce_head_kernel(const float* __restrict__ clip, int B, int rpb, const float* __restrict__ row_lse,
                 const float* __restrict__ chunk_part, int nblk, const float* __restrict__ Tptr,
                 float* __restrict__ g, double* __restrict__ blk_sums, unsigned int* __restrict__ ticket,
                 double* __restrict__ sums, float* __restrict__ out) {
@@ -174,8 +174,8 @@ nce_head_kernel(const float* __restrict__ clip, int B, const float* __restrict__
     __syncthreads();
 
     const int blk = blockIdx.x;
-    const int r0 = blk * kNceRowsPerBlock;
-    const int nr = min(kNceRowsPerBlock, B - r0);
+    const int r0 = blk * rpb;
+    const int nr = min(rpb, B - r0);
     const float inv2B = 0.5f / (float)B;
     double loss = 0.0, sd = 0.0, sd2 = 0.0, so = 0.0, so2 = 0.0, gc = 0.0;
     float mo = -INFINITY;
@@ -266,7 +266,7 @@ extern "C" int triad_infonce_partial(const float* clip_rows, int rows, int B, in
     cudaStream_t st = (cudaStream_t)stream;
     NceWs w = nce_ws_carve(ws, rows, B);
     const int nblk = nce_blocks(rows);
-    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip_rows, rows, B, row_lse, w.chunk_part, nullptr);
+    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip_rows, rows, B, kNceRowsPerBlock, row_lse, w.chunk_part, nullptr);
     TRIAD_LAUNCH_CHECK("nce_partial_kernel");
     nce_combine_kernel<<<ceil_div(B, 256), 256, 0, st>>>(w.chunk_part, nblk, B, 0, col_part);
     TRIAD_LAUNCH_CHECK("nce_combine_kernel");
@@ -293,10 +293,31 @@ extern "C" int triad_infonce_finish(const float* clip_rows, int rows, int B, int
     return TRIAD_OK;
 }
 
-// Workspace of the fused head: the partial/finish layout, then the ticket.
+// Fused head: rows per CTA.  Every CTA combines the column partials of ALL row blocks itself (2*nblk dependent-latency
+// loads per thread), so few blocks are better than many: about 16 (B = 256: 16 CTAs of 16 rows — measured 19 us with
+// 64 blocks of 4 rows, 28 us with the sharded path's 8 blocks of 32), never more than kHeadMaxBlocks.
+static inline int head_rows_per_block(int B) {
+    int rpb = 4;
+    while (ceil_div(B, rpb) > 16) rpb *= 2;
+    while (rpb > 32 && ceil_div(B, rpb / 2) <= kHeadMaxBlocks) rpb /= 2;     // large B: keep blocks <= 32 rows if the partials allow
+    return rpb;
+}
+struct HeadWs { float* chunk_part; float* row_lse; double* blk_sums; unsigned int* ticket; size_t total; };
+static inline HeadWs head_ws_carve(void* ws, int B) {
+    const size_t nblk = ceil_div(B, head_rows_per_block(B));
+    char* p = (char*)ws;
+    HeadWs w;
+    w.chunk_part = (float*)p; p += align_up(nblk * 2 * (size_t)B * 4, 256);
+    w.row_lse = (float*)p;    p += align_up((size_t)B * 4, 256);
+    w.blk_sums = (double*)p;  p += align_up(nblk * 8 * 8, 256);
+    w.ticket = (unsigned int*)p; p += 256;
+    w.total = (size_t)(p - (char*)ws);
+    return w;
+}
+
 extern "C" size_t triad_contrastive_head_workspace_bytes(int B) {
     if (B <= 0) return 0;
-    return nce_ws_bytes(B, B) + 256;
+    return head_ws_carve(nullptr, B).total;
 }
 
 extern "C" int triad_contrastive_head(const float* clip, int B, const float* temperature,
@@ -304,19 +325,17 @@ extern "C" int triad_contrastive_head(const float* clip, int B, const float* tem
                                       void* ws, size_t ws_bytes, void* stream) {
     if (!clip || !g || !sums || !out4 || !ws) return fail_msg(TRIAD_ERR_BAD_ARG, "contrastive_head: null pointer");
     if (B <= 0) return fail_msg(TRIAD_ERR_BAD_SHAPE, "contrastive_head: bad B");
+    if (B > kHeadMaxBlocks * 32 || (size_t)B * 4 > 96 * 1024)
+        return fail_msg(TRIAD_ERR_UNSUPPORTED, "contrastive_head: B too large for the fused head (use infonce_partial/finish)");
     if (ws_bytes < triad_contrastive_head_workspace_bytes(B)) return fail_msg(TRIAD_ERR_WORKSPACE, "contrastive_head: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    NceWs w = nce_ws_carve(ws, B, B);
-    const int nblk = nce_blocks(B);
-    unsigned int* ticket = (unsigned int*)((char*)ws + nce_ws_bytes(B, B));
-    float* row_lse = w.col_lse;          // the [B] slot is free here: the head keeps the column LSE in shared memory
-    if (nblk > kHeadMaxBlocks || (size_t)B * 4 > 96 * 1024) {
-        return fail_msg(TRIAD_ERR_UNSUPPORTED, "contrastive_head: B too large for the fused head (use infonce_partial/finish)");
-    }
-    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip, B, B, row_lse, w.chunk_part, ticket);
+    const HeadWs w = head_ws_carve(ws, B);
+    const int rpb = head_rows_per_block(B);
+    const int nblk = ceil_div(B, rpb);
+    nce_partial_kernel<<<nblk, kNceThreads, 0, st>>>(clip, B, B, rpb, w.row_lse, w.chunk_part, w.ticket);
     TRIAD_LAUNCH_CHECK("nce_partial_kernel");
-    nce_head_kernel<<<nblk, kNceThreads, (size_t)B * 4, st>>>(clip, B, row_lse, w.chunk_part, nblk, temperature, g,
-                                                              w.blk_sums, ticket, sums, out4);
+    nce_head_kernel<<<nblk, kNceThreads, (size_t)B * 4, st>>>(clip, B, rpb, w.row_lse, w.chunk_part, nblk, temperature, g,
+                                                              w.blk_sums, w.ticket, sums, out4);
     TRIAD_LAUNCH_CHECK("nce_head_kernel");
     return TRIAD_OK;
 }

@@ -22,6 +22,8 @@
 #include "common.cuh"
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace triad {
 
 template <typename T> struct Vec16;            // one 16-byte chunk of a row
@@ -339,8 +341,13 @@ dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, 
     uint32_t* tot = lbase + Nv;                                                           // [Nv]
     uint32_t* total_s = tot + Nv;
 
-    constexpr int kVec = 16 / (int)sizeof(IdxT);                  // rows per 16-byte load
+    // 4 rows per load and lane: a warp instruction covers 128 consecutive rows.  (16 rows per lane — one 16-byte load —
+    // was tried: fewer loads, but rows then reach the placement step far from row order — the order inside a
+    // 512-row window becomes (element, lane) — and the insertion sort of step 3b, which assumes almost sorted runs,
+    // grew to 45 % of the kernel: 164 us instead of 139.)
+    constexpr int kVec = 4;                                       // rows per load
     constexpr int kLoads = kGroupPerLane / kVec;                  // loads per lane (32 rows per lane)
+    using LoadT = typename std::conditional<sizeof(IdxT) == 1, uint32_t, uint2>::type;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int jl = blockIdx.x / n_groups, c = blockIdx.x - jl * n_groups;
     const int j = j0 + jl;
@@ -348,6 +355,15 @@ dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, 
     const IdxT* base = idx + (size_t)j * img_pitch;
 
     for (int k = tid; k < kGroupWarps * Nv; k += blockDim.x) hist[k] = 0;
+    // g[i][j] of the queries this group touches (<= kGroupRows/16 + 2 of them): step 4 looks its weights up here
+    // instead of issuing one scattered global load per entry (32 sectors per warp instruction)
+    __shared__ float gq_s[kGroupRows / 16 + 2];
+    const uint32_t i_first = fast_div((uint32_t)x_group, div_pad);
+    {
+        const int x_last = min(x_group + kGroupRows, Mpad) - 1;
+        const int nq_here = (int)fast_div((uint32_t)x_last, div_pad) - (int)i_first + 1;
+        for (int t = tid; t < nq_here; t += blockDim.x) gq_s[t] = g[(size_t)(i_first + t) * Bv + j];
+    }
     __syncthreads();
 
     // ---- 1. every lane fetches its 32 winners (kLoads independent vector loads), then the per-warp histogram.
@@ -356,22 +372,23 @@ dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, 
     uint32_t pv[kGroupPerLane / 2];
     uint32_t* myh = hist + warp * Nv;
     {
-        uint4 raw[kLoads];
+        LoadT raw[kLoads];
 #pragma unroll
         for (int v = 0; v < kLoads; ++v) {
             const int x = x_group + warp * (kGroupPerLane * 32) + v * 32 * kVec + lane * kVec;
-            raw[v] = make_uint4(0u, 0u, 0u, 0u);
-            if (x < Mpad) raw[v] = __ldg(reinterpret_cast<const uint4*>(base + x));        // nq_pad % 16 == 0: never straddles
+            raw[v] = LoadT();
+            if (x < Mpad) raw[v] = __ldg(reinterpret_cast<const LoadT*>(base + x));        // nq_pad % 16 == 0: never straddles
         }
 #pragma unroll
         for (int v = 0; v < kLoads; ++v) {
             const int x = x_group + warp * (kGroupPerLane * 32) + v * 32 * kVec + lane * kVec;
             const uint32_t qi = fast_div((uint32_t)x, div_pad);
             const int a0 = x - (int)qi * nq_pad;
-            const uint32_t w32[4] = {raw[v].x, raw[v].y, raw[v].z, raw[v].w};
+            uint32_t w32[2];
+            if constexpr (sizeof(IdxT) == 1) { w32[0] = raw[v]; w32[1] = 0u; } else { w32[0] = raw[v].x; w32[1] = raw[v].y; }
 #pragma unroll
             for (int e = 0; e < kVec; ++e) {
-                uint32_t p = sizeof(IdxT) == 1 ? (w32[e >> 2] >> (8 * (e & 3))) & 0xffu : (w32[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+                uint32_t p = sizeof(IdxT) == 1 ? (w32[0] >> (8 * e)) & 0xffu : (w32[e >> 1] >> (16 * (e & 1))) & 0xffffu;
                 bool ok = x < Mpad && a0 + e < Nq;
                 if (masked && ok) ok = row_scale[(size_t)qi * Nq + a0 + e] != 0.f;
                 if (!ok) p = 0xffffu;
@@ -434,13 +451,13 @@ dv_group_sort_kernel(const IdxT* __restrict__ idx, const float* __restrict__ g, 
     // ---- 4. the group's list leaves as one contiguous run; the (unpadded) row number and the weight are attached here ----
     const uint32_t n = *total_s;
     DvEntry* out = entries + (size_t)blockIdx.x * kGroupRows;
-    const float* gj = g + j;
+    const float rs_uniform = masked ? 0.f : row_scale[0];                      // no mask: every row weighs 1/Nq
 #pragma unroll 8
     for (uint32_t t = tid; t < n; t += kGroupWarps * 32) {
         const uint32_t x = (uint32_t)x_group + (uint32_t)sorted[t];
         const uint32_t i = fast_div(x, div_pad);
         const uint32_t r = x - i * (uint32_t)(nq_pad - Nq);                    // i*Nq + a
-        DvEntry d; d.row = r; d.w = row_scale[r] * gj[(size_t)i * Bv];
+        DvEntry d; d.row = r; d.w = (masked ? row_scale[r] : rs_uniform) * gq_s[i - i_first];
         out[t] = d;
     }
 }
@@ -834,9 +851,19 @@ static int bwd_typed(const void* q, const void* v, const void* idx, const float*
     const int kch = ceil_div(D / E, 32);
     if (dq && (kch < 1 || kch > 4)) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_bwd: D too large (max 1024 bf16 / 512 fp32)");
     if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_pipe_supported(Nv, D, TRIAD_DTYPE_BF16) &&
-        !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1 | TRIAD_BWD_DQ_STAGED | TRIAD_BWD_PACK_ROWS))) {
-        // the software-pipelined shared-memory gather (bwd_dq_pipe.cu)
-        const int rc = launch_dq_pipe(v, idx, g, row_scale, Tp, Bq, Bv, Nq, Nv, D, dq, (int*)ws, nullptr, nullptr, dq_pipe_variant(), st);
+        !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1 | TRIAD_BWD_DQ_STAGED))) {
+        // the software-pipelined shared-memory gather (bwd_dq_pipe.cu); TRIAD_BWD_PACK_ROWS (masked text queries): only
+        // the 8-row groups that hold a row with a non-zero weight are swept
+        const int* glist = nullptr;
+        const int* n_groups = nullptr;
+        if (bwd_flags & TRIAD_BWD_PACK_ROWS) {
+            void* maps = (char*)ws + pack_maps_offset;
+            const int rcm = launch_pack_groups(row_scale, Bq, Nq, maps, st);
+            if (rcm) return rcm;
+            n_groups = (const int*)maps + Bq;
+            glist = (const int*)maps + Bq + 1;
+        }
+        const int rc = launch_dq_pipe(v, idx, g, row_scale, Tp, Bq, Bv, Nq, Nv, D, dq, (int*)ws, glist, n_groups, dq_pipe_variant(), st);
         if (rc) return rc;
     } else if (dq && sizeof(T) == 2 && sizeof(IdxT) == 1 && dq_smem_supported(Nv, D, TRIAD_DTYPE_BF16) &&
         !(bwd_flags & (TRIAD_BWD_GENERIC_DQ | TRIAD_BWD_DQ_L1))) {
@@ -1012,6 +1039,7 @@ extern "C" int triad_maxmean_bwd(const void* q, const void* v, const void* idx, 
         return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_bwd: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     TRIAD_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, st));      // abort flag + dT ticket
+    if (flags & TRIAD_BWD_TEST_TRIP_WATCHDOG) TRIAD_CUDA_CHECK(cudaMemsetAsync(ws, 1, 4, st));
     const bool wide = Nv > 256;
     const size_t pmo = triad_maxmean_bwd_workspace_bytes(Bq, Bv, Nq, Nv, D, dtype) - pack_map_bytes(Bq, Nq);
     if (dtype == TRIAD_DTYPE_BF16) {

@@ -42,8 +42,10 @@ int launch_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, cuda
 // ---------------------------------------------------------------------------------------
 // finalize: clip[i][j] = sum over the 32-row groups that hold rows of query i
 // ---------------------------------------------------------------------------------------
+// A tripped pipeline watchdog (abort flag != 0: the forward kernel drained out and left partial sums unwritten) must
+// not pass silently: clip becomes NaN, so the loss — and everything the caller logs — is NaN.
 __global__ void finalize_clip_kernel(const float* __restrict__ part, int Bq, int Bv, int Nq,
-                                     int G, int S, float* __restrict__ clip) {
+                                     int G, int S, float* __restrict__ clip, const int* __restrict__ abort_flag) {
     const int nib = (Bq + blockDim.x - 1) / blockDim.x;
     const int i = (blockIdx.x % nib) * blockDim.x + threadIdx.x;
     const int j = blockIdx.x / nib;
@@ -56,20 +58,21 @@ __global__ void finalize_clip_kernel(const float* __restrict__ part, int Bq, int
         const int qfirst = (g * 32) / Nq;
         acc += pj[(size_t)g * S + (i - qfirst)];
     }
+    if (abort_flag && *abort_flag != 0) acc = __int_as_float(0x7fc00000);
     clip[(size_t)i * Bv + j] = acc;
 }
 
-int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, cudaStream_t st) {
+int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, const int* abort_flag, cudaStream_t st) {
     PartLayout pl = part_layout(Bq * Nq, Nq);
     dim3 grid((unsigned)(ceil_div(Bq, 128) * Bv));
-    finalize_clip_kernel<<<grid, 128, 0, st>>>(part, Bq, Bv, Nq, pl.G, pl.S, clip);
+    finalize_clip_kernel<<<grid, 128, 0, st>>>(part, Bq, Bv, Nq, pl.G, pl.S, clip, abort_flag);
     TRIAD_LAUNCH_CHECK("finalize_clip_kernel");
     return TRIAD_OK;
 }
 
 // packed rows: clip[i][j] = sum of the query's pieces (one per 32-row group its kept rows touch), ascending
 __global__ void finalize_clip_packed_kernel(const float* __restrict__ part, const int* __restrict__ off, int Bq, int Bv,
-                                            int pieces, float* __restrict__ clip) {
+                                            int pieces, float* __restrict__ clip, const int* __restrict__ abort_flag) {
     const int nib = (Bq + blockDim.x - 1) / blockDim.x;
     const int i = (blockIdx.x % nib) * blockDim.x + threadIdx.x;
     const int j = blockIdx.x / nib;
@@ -81,12 +84,14 @@ __global__ void finalize_clip_packed_kernel(const float* __restrict__ part, cons
         const float* pp = part + ((size_t)j * Bq + i) * pieces;
         for (int s = 0; s < np; ++s) acc += pp[s];
     }
+    if (abort_flag && *abort_flag != 0) acc = __int_as_float(0x7fc00000);
     clip[(size_t)i * Bv + j] = acc;
 }
 
-int launch_finalize_clip_packed(const float* part, const int* pack_off, int Bq, int Bv, int Nq, float* clip, cudaStream_t st) {
+int launch_finalize_clip_packed(const float* part, const int* pack_off, int Bq, int Bv, int Nq, float* clip,
+                                const int* abort_flag, cudaStream_t st) {
     dim3 grid((unsigned)(ceil_div(Bq, 128) * Bv));
-    finalize_clip_packed_kernel<<<grid, 128, 0, st>>>(part, pack_off, Bq, Bv, packed_pieces(Nq), clip);
+    finalize_clip_packed_kernel<<<grid, 128, 0, st>>>(part, pack_off, Bq, Bv, packed_pieces(Nq), clip, abort_flag);
     TRIAD_LAUNCH_CHECK("finalize_clip_packed_kernel");
     return TRIAD_OK;
 }

@@ -78,6 +78,53 @@ pack_copy_kernel(const uint4* __restrict__ q, const int* __restrict__ rowmap, co
     }
 }
 
+// ---- 8-row groups for the pipelined dq (bwd_dq_pipe.cu): the groups (i, a0 = 0, 8, 16, ...) that hold at least one
+// kept row, as padded row indices x0 = i*nq_pad + a0, in order; goff[Bq] = number of active groups -----------------
+__device__ __forceinline__ bool group_active(const float* __restrict__ rs, int Nq, int a0) {
+    bool any = false;
+    for (int a = a0; a < min(a0 + 8, Nq); ++a) any |= rs[a] != 0.f;
+    return any;
+}
+__global__ void __launch_bounds__(256)
+pack_group_count_kernel(const float* __restrict__ row_scale, int Bq, int Nq, int* __restrict__ cnt) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= Bq) return;
+    int c = 0;
+    for (int a0 = lane * 8; a0 < Nq; a0 += 256) c += group_active(row_scale + (size_t)i * Nq, Nq, a0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[i] = c;
+}
+__global__ void __launch_bounds__(256)
+pack_group_map_kernel(const float* __restrict__ row_scale, const int* __restrict__ goff, int Bq, int Nq, int nq_pad,
+                      int* __restrict__ glist) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= Bq) return;
+    int k = goff[i];
+    for (int base = 0; base < Nq; base += 256) {
+        const int a0 = base + lane * 8;
+        const bool keep = a0 < Nq && group_active(row_scale + (size_t)i * Nq, Nq, a0);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) glist[k + __popc(m & ((1u << lane) - 1u))] = i * nq_pad + a0;
+        k += __popc(m);
+    }
+}
+
+// maps (inside the pack_map_bytes region): goff[Bq+1] | glist[Bq*ceil(Nq/8)] | cnt[Bq]
+int launch_pack_groups(const float* row_scale, int Bq, int Nq, void* maps, cudaStream_t st) {
+    int* goff = (int*)maps;
+    int* glist = goff + Bq + 1;
+    int* cnt = glist + (size_t)Bq * ceil_div(Nq, 8);
+    const int blocks = ceil_div(Bq * 32, 256);
+    pack_group_count_kernel<<<blocks, 256, 0, st>>>(row_scale, Bq, Nq, cnt);
+    TRIAD_LAUNCH_CHECK("pack_group_count_kernel");
+    pack_scan_kernel<<<1, 1024, 0, st>>>(cnt, Bq, goff);
+    TRIAD_LAUNCH_CHECK("pack_scan_kernel");
+    pack_group_map_kernel<<<blocks, 256, 0, st>>>(row_scale, goff, Bq, Nq, nq_padded(Nq), glist);
+    TRIAD_LAUNCH_CHECK("pack_group_map_kernel");
+    return TRIAD_OK;
+}
+
 // scratch layout of the packing maps: off[Bq+1] | rowmap[M] (ints; off[Bq] = M')
 size_t pack_map_bytes(int Bq, int Nq) { return align_up(((size_t)Bq + 1 + (size_t)Bq * Nq) * 4 + (size_t)Bq * 4, 256); }
 

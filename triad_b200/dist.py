@@ -238,6 +238,41 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
     return out
 
 
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int):
+    """Top-k of candidate (score, global id) pairs under the library's retrieval order: score descending, ties to the
+    lower id (retrieve.cu::make_key; a stable argsort of -scores over ids in ascending order, retrieval.py:125)."""
+    by_id = torch.argsort(ids, stable=True)
+    s, i = scores[by_id], ids[by_id]
+    order = torch.argsort(s, descending=True, stable=True)[:k]
+    return s[order], i[order]
+
+
+def sharded_retrieve_topk(q_feats: torch.Tensor, gallery_shard: torch.Tensor, temperature, k: int, id0: int,
+                          group=None, direction: int = 0, local_topk=None):
+    """BASELINE cfg 5 across GPUs (replaces the gallery loop of retrieval.py:161-175): the gallery is
+    sharded BY IMAGES — this rank holds images [id0, id0 + n_local) — every rank scores the (replicated) query against
+    its shard and keeps its local top-k, the k (score, global id) pairs of every rank are all-gathered (2*k*W numbers)
+    and merged with the single-GPU ordering.  Returns (scores fp32 [k], ids int64 [k]), identical on every rank and
+    bit-identical to retrieve_topk over the whole gallery on one GPU.
+
+    `local_topk(q, gallery, temperature, k, direction) -> (scores, local ids)` is the scoring kernel (the CUDA
+    retrieve_topk by default; the CPU tests inject an oracle-backed stand-in)."""
+    if local_topk is None:
+        from .retrieval import retrieve_topk as local_topk
+    W = dist.get_world_size(group) if dist.is_initialized() else 1
+    n_local = gallery_shard.shape[0]
+    kl = min(k, n_local)
+    s, ids = local_topk(q_feats, gallery_shard, temperature, kl, direction)
+    cand_s = torch.full((k,), float("-inf"), dtype=torch.float32, device=s.device)
+    cand_i = torch.full((k,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=s.device)
+    cand_s[:kl] = s.float()
+    cand_i[:kl] = ids.to(torch.int64) + int(id0)
+    if W > 1:
+        cand_s = _all_gather(cand_s, W, group).reshape(-1)
+        cand_i = _all_gather(cand_i, W, group).reshape(-1)
+    return merge_topk(cand_s, cand_i, k)
+
+
 class ShardedContrastiveLoss(torch.autograd.Function):
     """Autograd face of sharded_contrastive_step: the forward computes the loss AND the gradients
     (the saved argmax indices never outlive the call); backward scales them by the incoming grad.
