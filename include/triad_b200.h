@@ -209,6 +209,26 @@ int triad_diag_ranks(const float* sim, int N, int32_t* ranks, void* stream);
 int triad_similarity_matrix(const float* f1, const float* f2, const float* temperature,
                             int B, int N1, int N2, int D, float* out, void* stream);
 
+/* ---- producers of the hot path's inputs -------------------------------- */
+/* The projection head of the audio / text / visual embedders, fused: replaces
+ *   projection2(layer_norm(projection1(x)))     model.py:32-34,68 / :81-83,116 / :253-255,326
+ * and, with l2_normalize != 0, the F.normalize(feats, dim=-1) of retrieval.py:93-94.
+ * x bf16 [M, Din] (token rows of the encoder output, flattened over the batch), w1 bf16 [512, Din] and w2 bf16
+ * [Dout, 512] in nn.Linear's own [out, in] layout, b1 / ln_g / ln_b fp32 [512], b2 fp32 [Dout]; out bf16 [M, Dout],
+ * i.e. [B, N, D] with D innermost — the layout triad_maxmean_fwd reads.  Arithmetic follows the reference under
+ * autocast: bf16 GEMMs with fp32 accumulation, Linear outputs rounded to bf16, LayerNorm in fp32.
+ * Din % 64 == 0, Dout % 16 == 0, Dout <= 512.  ws: triad_project_workspace_bytes(). */
+size_t triad_project_workspace_bytes(void);
+int triad_project_tokens(const void* x, const void* w1, const float* b1, const float* ln_g, const float* ln_b,
+                         float ln_eps, const void* w2, const float* b2, int M, int Din, int Dout, int l2_normalize,
+                         void* out, void* ws, size_t ws_bytes, void* stream);
+/* Patch dropout's compaction (model.py:283-307 without the per-image loop): for every image the patches with
+ * keep[b][n] != 0 are copied, in order, to the front of out[b] ([B, max_len, D], same element type as x) and the
+ * remaining rows are zero-filled.  max_len >= the largest kept count (the caller sizes the output, as the
+ * reference's max(...) does).  D*elt_bytes % 16 == 0. */
+int triad_patch_compact(const void* x, const uint8_t* keep, int B, int N, int D, int elt_bytes, int max_len,
+                        void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

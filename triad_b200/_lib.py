@@ -61,6 +61,10 @@ SIGNATURES = {
     "triad_diag_ranks": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "triad_similarity_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p]),
+    "triad_project_workspace_bytes": (c_size_t, []),
+    "triad_project_tokens": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "triad_patch_compact": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None
