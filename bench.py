@@ -573,6 +573,9 @@ def run_triad(args, cfg_key):
         del q4, v4
         torch.cuda.empty_cache()
 
+        # ---- f3: the fused projection head on the audio shape of cfg 2 (64 000 HuBERT frames, 768 -> 512 -> 512) -----
+        extras["f3_projection_head"] = f3_block(dev, local, peaks, timed)
+
         # ---- cfg 5: one query against a 104.9 GB gallery, forward-only top-k (HBM-bound for text queries) ---------
         if not args.no_cfg5:
             extras["cfg5"] = cfg5_block(dev, local, peaks, 1, 0, timed)
@@ -611,6 +614,36 @@ def run_triad(args, cfg_key):
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+def f3_block(dev, local, peaks, timed):
+    """projection2(layer_norm(projection1(x))) for B=256 x 250 frames, Din=768, as one launch
+    (triad_project_tokens), next to torch.nn's three kernels under autocast on the same weights."""
+    import torch
+    from triad_b200.producers import ProjectionHead
+    B, N, Din, Dout = 256, 250, 768, 512
+    torch.manual_seed(3)
+    head = ProjectionHead(Din, Dout).to(dev)
+    xs = [torch.randn(B, N, Din, device=dev).bfloat16() for _ in range(3)]
+
+    def torch_head(x):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return head.projection2(head.layer_norm(head.projection1(x)))
+
+    with torch.no_grad():
+        y = head(xs[0]); ref = torch_head(xs[0])
+        err = ((y.float() - ref.float()).norm() / ref.float().norm()).item()
+        for i in range(3):
+            head(xs[i])
+        with ClockSampler(local) as ck:
+            ms = timed(lambda i: head(xs[i % 3]), 30)
+        for i in range(3):
+            torch_head(xs[i])
+        ms_t = timed(lambda i: torch_head(xs[i % 3]), 30)
+    flops = 2.0 * B * N * (Din * 512 + 512 * Dout)
+    return {"workload": f"projection head, {B}x{N} tokens, {Din} -> 512 -> LayerNorm -> {Dout}, bf16, one launch",
+            "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": flops / (ms * 1e-3) / 1e12 / peaks["bf16"],
+            "torch_nn_autocast_ms": ms_t, "rel_err_vs_torch_nn_autocast": err, "clocks": ck.summary()}
 
 
 def cfg5_block(dev, local, peaks, world, rank, timed):

@@ -803,3 +803,34 @@ def test_tripped_watchdog_is_loud():
     assert bool(torch.isnan(dq.float()).all())
     dq, dv, dT = ops.maxmean_bwd(qd, vd, idx, g, clip, scale, Tt)
     assert bool(torch.isfinite(dq.float()).all())
+
+
+def test_dense_regulariser_with_patch_dropout_shapes(monkeypatch):
+    """Patch dropout leaves Nv ~ 190-210 patches (model.py:296-307), not a multiple of 8: the tcgen05 dense-regulariser
+    forward still takes the shape (images padded with zero patches, which contribute exactly nothing) and agrees with
+    the library-GEMM path and with fp64 autograd."""
+    from triad_b200 import regularizers as R
+    B, Nq, Nv, D, T, lo = 5, 60, 201, 128, 1.5, -60.0
+    g = torch.Generator().manual_seed(8)
+    q = (torch.randn(B, Nq, D, generator=g) * 0.4).bfloat16()
+    v = (torch.randn(B, Nv, D, generator=g) * 0.4).bfloat16()
+    assert R.fused_supported(q.cuda(), v.cuda())
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(R, "USE_FUSED", fused)
+        qd, vd = q.cuda().requires_grad_(), v.cuda().requires_grad_()
+        Td = torch.nn.Parameter(torch.tensor(T, device="cuda"))
+        val = R.nonneg_pressure(qd, vd, Td, lo)
+        val.backward()
+        outs[fused] = (val.item(), qd.grad, vd.grad, Td.grad.item())
+        assert vd.grad.shape == (B, Nv, D)
+    q64, v64 = q.double().requires_grad_(), v.double().requires_grad_()
+    T64 = torch.tensor(T, dtype=torch.float64, requires_grad=True)
+    ref = (torch.einsum("iad,jpd->ijap", q64, v64) * T64).clamp(min=lo, max=0).pow(2).mean()
+    ref.backward()
+    for fused in (True, False):
+        val, dq, dv, dT = outs[fused]
+        assert abs(val - ref.item()) <= 1e-2 * ref.item()
+        assert rel_err(dq.double().cpu(), q64.grad) < 1e-2 and rel_err(dv.double().cpu(), v64.grad) < 1e-2
+        assert abs(dT - T64.grad.item()) <= 1e-2 * abs(T64.grad.item())
+    assert rel_err(outs[True][1], outs[False][1]) < 4e-3 and rel_err(outs[True][2], outs[False][2]) < 4e-3

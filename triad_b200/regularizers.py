@@ -48,8 +48,12 @@ USE_FUSED = True
 
 
 def fused_supported(q: torch.Tensor, v: torch.Tensor) -> bool:
+    """Shapes the tcgen05 dense-regulariser forward takes.  Patch counts that are not a multiple of 8 (patch dropout:
+    Nv ~ 190-210, model.py:296-307) are handled by nonneg_sweep, which pads the images with ZERO patches: a zero
+    patch has S = 0, clamp(0, lo, 0)^2 = 0 and a zero gradient, so value and gradients are exactly those of the
+    unpadded problem (the mean's denominator is passed explicitly)."""
     D, Nv = q.shape[-1], v.shape[1]
-    return q.dtype == torch.bfloat16 and D % 64 == 0 and D <= 512 and Nv <= 256 and Nv % 8 == 0
+    return q.dtype == torch.bfloat16 and D % 64 == 0 and D <= 512 and (Nv + 7) // 8 * 8 <= 256
 
 
 def nonneg_fused_chunk(q: torch.Tensor, vc: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write_grad: bool,
@@ -77,14 +81,17 @@ def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, n
     rows are one rank's shard)."""
     q, v = q.contiguous(), v.contiguous()
     Bq, Nq, D = q.shape
-    Bv, Nv, _ = v.shape
+    Bv, Nv_true, _ = v.shape
+    fused = USE_FUSED and fused_supported(q, v)
+    if fused and Nv_true % 8:                                # zero patches up to a multiple of 8 (exact, see fused_supported)
+        v = torch.nn.functional.pad(v, (0, 0, 0, 8 - Nv_true % 8))
+    Nv = v.shape[1]
     M = Bq * Nq
     q2 = q.view(M, D)
     sums = torch.zeros(2, dtype=torch.float64, device=q.device)
     jc = max(1, min(Bv, int(chunk_bytes) // max(1, M * Nv * q.element_size())))
     dq32 = torch.zeros(M, D, dtype=torch.float32, device=q.device) if need_grads else None
     dv = torch.empty_like(v) if need_grads else None
-    fused = USE_FUSED and fused_supported(q, v)
     for j0 in range(0, Bv, jc):
         vc = v[j0:j0 + jc].reshape(-1, D)
         if fused:       # the tcgen05 forward writes N itself (no S chunk, no elementwise pass)
@@ -95,6 +102,8 @@ def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, n
         if need_grads:
             dq32.add_(torch.mm(S, vc))
             dv[j0:j0 + jc] = torch.mm(S.t(), q2).view(-1, Nv, D)
+    if dv is not None and Nv != Nv_true:
+        dv = dv[:, :Nv_true].contiguous()
     return sums, dq32, dv
 
 
