@@ -475,7 +475,8 @@ def run_triad(args, cfg_key):
                 "peak_source": f"{peaks['source']}: burst; sustained {peaks['bf16_sustained']}",
                 "frac_of_sustained": achieved / peaks["bf16_sustained"], "ms": fwd_ms, "traffic": traffic,
                 "algorithmic_flops_per_launch": f_fwd, "step_flops": f_fwd + f_bwd,
-                "step_frac_of_peak": (f_fwd + f_bwd) / (step_ms * 1e-3) / 1e12 / peaks["bf16"]}
+                "step_frac_of_peak": (f_fwd + f_bwd) / (step_ms * 1e-3) / 1e12 / peaks["bf16"],
+                "step_frac_of_sustained_peak": (f_fwd + f_bwd) / (step_ms * 1e-3) / 1e12 / peaks["bf16_sustained"]}
 
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -488,6 +489,26 @@ def run_triad(args, cfg_key):
     fwd_ev.clear()
 
     extras = {}
+    if world == 1 and not args.no_extras and cfg_key == "cfg2":
+        # ---- burst vs. sustained: the same step, 60 back to back from an idle GPU, timed one by one ----
+        torch.cuda.synchronize()
+        time.sleep(2.0)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(61)]
+        with ClockSampler(local) as ck:
+            evs[0].record()
+            for i in range(60):
+                step(*sets[i % n_sets])
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(60)]
+        f_all = sum(algorithmic_flops(B, tokens_local, cfg["Nv"], cfg["D"]))
+        extras["burst_vs_sustained"] = {
+            "what": "60 steps back to back after 2 s of idle, each step timed with its own CUDA events: the first ~50 ms run at "
+                    "boost clocks, then the power governor (sw_power_cap) lowers the SM clock for the whole step",
+            "first_10_steps_ms": sum(per[1:11]) / 10, "last_10_steps_ms": sum(per[-10:]) / 10,
+            "first_10_frac_of_burst_peak": f_all / (sum(per[1:11]) / 10 * 1e-3) / 1e12 / peaks["bf16"],
+            "last_10_frac_of_sustained_peak": f_all / (sum(per[-10:]) / 10 * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            "per_step_ms": [round(x, 3) for x in per], "clocks": ck.summary()}
     if world == 1 and not args.no_extras:
         # ---- the reference's FULL loss (contrastive + regularisers), reported beside the metric ----
         model.triad_regularizers = True

@@ -2,7 +2,7 @@
 """Kernel timeline of one steady-state step (torch.profiler / CUPTI activity records, no replay): start, duration
 and the idle gap before every kernel — where the step's time goes BETWEEN kernels.
 
-    python tools/timeline.py [cfg2] [steps=6]
+    python tools/timeline.py [cfg2] [steps=6] [full]       # full: with the reference's regularisers on
 """
 import os
 import sys
@@ -25,7 +25,7 @@ def main():
     for s in sets:
         s[0].requires_grad_(True); s[1].requires_grad_(True)
     m = triad_b200.TriadHotPath(1.5).to(dev)
-    m.triad_regularizers = False
+    m.triad_regularizers = len(sys.argv) > 3 and sys.argv[3] == "full"
 
     def step(q, v, mask):
         q.grad = v.grad = m.temperature.grad = None

@@ -141,6 +141,17 @@ def _stats_from_sums(sums: torch.Tensor, B: int, prefix: str) -> Dict[str, float
     }
 
 
+_zeros: Dict[torch.device, torch.Tensor] = {}
+
+
+def _zero_scalar(device) -> torch.Tensor:
+    """A constant fp32 zero on `device` (the 0.01*l_smooth slot when the regularisers are off): made once, not per step."""
+    z = _zeros.get(device)
+    if z is None:
+        z = _zeros[device] = torch.zeros((), dtype=torch.float32, device=device)
+    return z
+
+
 class TriadSimilarityMixin:
     """Provides compute_all_similarities_{av,tv}, compute_contrastive_loss_{av,tv} and
     compute_similarity_matrix with the reference's signatures."""
@@ -257,8 +268,7 @@ class TriadSimilarityMixin:
         if self._dense_terms_enabled(token_sims):
             reg, smooth = self._regularization_av(token_sims, l_cal)
             return contrastive + reg, contrastive, reg, smooth, stats
-        smooth = torch.zeros((), dtype=torch.float32, device=contrastive.device)
-        return con_plus_cal, contrastive, l_cal, smooth, stats
+        return con_plus_cal, contrastive, l_cal, _zero_scalar(contrastive.device), stats
 
     def compute_contrastive_loss_tv(self, clip_sims, token_sims):
         """(total, stats) — model.py:544-593 (see compute_contrastive_loss_av for the regulariser switch)."""
