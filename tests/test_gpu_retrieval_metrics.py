@@ -96,7 +96,7 @@ def test_av_metric_driver_matches_the_reference(ref_retrieval, tmp_path, monkeyp
     assert set(got) == set(want) and len(got) == 8
     for k in want:
         assert got[k] == pytest.approx(want[k], abs=1e-12), k
-    assert want["A->V_r20"] >= want["A->V_r1"] and want["A->V_r1"] > 1.0 / N_ITEMS      # better than chance: items do match
+    assert 0.0 < want["A->V_r20"] < 1.0 and want["A->V_r20"] >= want["A->V_r1"]          # neither trivially 0 nor 1
 
 
 def test_tv_metric_driver_matches_the_reference(ref_retrieval, tmp_path, monkeypatch):
