@@ -184,6 +184,21 @@ int triad_nonneg_fused_chunk(const void* q, const void* v, const float* temperat
                              void* n_out, long long ldn, int write_grad, double* sums,
                              void* ws, size_t ws_bytes, void* stream);
 
+/* Regularisers on the B POSITIVE pairs only (token_sims[i,i]): temporal smoothness (mode 0, model.py:394-408:
+ * mean over (i, a < Nq-1, p) of (S[i,a+1,p] - S[i,a,p])^2) and patch-usage sparsity (mode 1, model.py:528-541:
+ * softmax over patches, usage fraction per patch over ALL Nq token rows, mean of relu(frac - threshold)^2).
+ * `raw` [B,Nq,Nv] (`dtype`) holds the raw dot products <q[i,a], v[i,p]> of the diagonal blocks (one small batched
+ * library GEMM); S = round(T*raw) as in model.py:387.  One pass writes G = d value / d raw (same shape and dtype; the
+ * operand of the two small backward GEMMs dq_i = G_i v_i, dv_i = G_i^T q_i) and sums[0] = value,
+ * sums[1] = d value / dT.  Replaces ~40 ATen kernels of the reference's autograd graph.  Deterministic. */
+size_t triad_pospair_workspace_bytes(int B);
+int triad_pospair_terms(const void* raw, int dtype, const float* temperature, int mode, float threshold,
+                        int B, int Nq, int Nv, void* G, double* sums, void* ws, size_t ws_bytes, void* stream);
+
+/* y[k] = x[k] * (*scale) for n elements of `dtype`; `scale` is an fp32 scalar in DEVICE memory (the upstream
+ * gradient of a loss term inside autograd's backward: no host synchronisation).  x == y is allowed. */
+int triad_scale(const void* x, void* y, size_t n, int dtype, const float* scale, void* stream);
+
 /* ---- retrieval: one query against a gallery, top-k ---------------------------------- */
 /* Replaces the per-pair aggregators retrieval.py:106-110 / :190-193 (direction 0:
  * mean_q max_p) and :112-115 / :195-198 (direction 1: mean_p max_q) and the python double

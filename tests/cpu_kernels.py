@@ -69,6 +69,23 @@ def _nonneg_cpu(q, v, T, lo, numel):
 OracleKernels.nonneg = lambda self, q, v, T, lo, numel: _nonneg_cpu(q, v, T, lo, numel)
 
 
+def _pospair_cpu(q, v, T, kind, threshold):
+    """fp64 autograd of the positive-pair term over these pairs (model.py:394-408 / :528-541), unweighted."""
+    q64, v64 = q.double().requires_grad_(), v.double().requires_grad_()
+    T64 = torch.tensor(float(T), dtype=torch.float64, requires_grad=True)
+    diag = torch.bmm(q64, v64.transpose(1, 2)) * T64
+    if kind == "av":
+        term = ((diag[:, 1:] - diag[:, :-1]) ** 2).mean()
+    else:
+        probs = torch.softmax(diag, dim=-1)
+        term = (torch.relu(probs.sum(dim=1) / probs.shape[1] - threshold) ** 2).mean()
+    term.backward()
+    return term.detach(), q64.grad.to(q.dtype), v64.grad.to(v.dtype), T64.grad
+
+
+OracleKernels.pospair = lambda self, q, v, T, kind, threshold: _pospair_cpu(q, v, T, kind, threshold)
+
+
 class PipelinedOracleKernels(OracleKernels):
     """Adds the split dv / dq entry points, so the sharded step takes its pipelined (per-destination reduce) path."""
 

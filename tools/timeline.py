@@ -5,6 +5,7 @@ and the idle gap before every kernel — where the step's time goes BETWEEN kern
     python tools/timeline.py [cfg2] [steps=6] [full]       # full: with the reference's regularisers on
 """
 import os
+import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -47,7 +48,8 @@ def main():
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     # the last full step: from the last-but-one forward kernel to the last one
-    fw = [k for k, e in enumerate(evs) if "maxmean_tc_kernel" in e.name]
+    # (the contrastive forward only: the dense-regulariser passes are the same kernel with kEmitN = true)
+    fw = [k for k, e in enumerate(evs) if re.search(r"maxmean_tc_kernel<\d, (false|true), false>", e.name)]
     a, b = fw[-2], fw[-1]
     t0 = evs[a].time_range.start
     prev_end = None

@@ -77,8 +77,18 @@ class CudaKernels:
         """Dense non-negative-pressure term of this rank's rows against ALL images, normalised by the global pair
         count: (sum clamp^2 fp64 scalar, dq (Bq,Nq,D), dv partial (Bv,Nv,D) fp32, dT fp64 scalar)."""
         from . import regularizers as R
-        sums, dq32, dv = R.nonneg_sweep(q, v, T, lo, numel, True, R.CHUNK_BYTES)
-        return sums[0], dq32.view(q.shape).to(q.dtype), dv.float(), sums[1]
+        sums, dq, dv = R.nonneg_sweep(q, v, T, lo, numel, True, R.CHUNK_BYTES)
+        return sums[0], dq.view(q.shape).to(q.dtype), dv.float(), sums[1]
+
+    def pospair(self, q, v, T, kind, threshold):
+        """Positive-pair term of this rank's pairs (mean over ITS pairs): temporal smoothness ("av") or patch-usage
+        sparsity ("tv").  Returns (value fp64 scalar, dq (Bl,Nq,D), dv (Bl,Nv,D), dT fp64 scalar), unweighted."""
+        from . import regularizers as R
+        qd, vd = q.detach().requires_grad_(True), v.detach().requires_grad_(True)
+        Td = T.detach().clone().requires_grad_(True)
+        term = R.temporal_smoothness(qd, vd, Td) if kind == "av" else R.patch_sparsity(qd, vd, Td, threshold)
+        term.backward()
+        return term.detach().double(), qd.grad, vd.grad, Td.grad.double()
 
 
 def _all_gather(x: torch.Tensor, W: int, group) -> torch.Tensor:
@@ -182,7 +192,7 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
       dense non-negative pressure   this rank's rows against all (all-gathered) images; value all-reduced, dq local,
                                     the dv partial reduce-scattered like the contrastive one;
       positive-pair terms           (temporal smoothness / patch sparsity on token_sims[i,i]) are local — a rank owns
-                                    both members of its positive pairs — and use the reference's ATen ops;
+                                    both members of its positive pairs (triad_pospair_terms);
       temperature calibration       a scalar on T ("av" only).
 
     Returns {reg, smooth (0.01*l_smooth, "av"), dq (Bl,Nq,D), dv (Bl,Nv,D), dT (this rank's share), dT_global}."""
@@ -205,21 +215,18 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
     s2, dq_nn, dv_nn_partial, dT_nn = k.nonneg(q_local, v_all, T, lo, numel)
     dv_nn = _reduce_scatter_rows(dv_nn_partial, W, r, group) if W > 1 else dv_nn_partial
 
-    # positive pairs: the reference's own ops on this rank's diagonal blocks; the global mean is the mean of the
-    # per-rank means (equal shard sizes)
-    ql, vl = q_local.clone().requires_grad_(True), v_local.clone().requires_grad_(True)
-    Tl = T.clone().requires_grad_(True)
-    diag = R.positive_pair_token_sims(ql, vl, Tl)
-    if kind == "av":
-        term = R.temporal_smoothness(diag) if Nq > 1 else diag.sum() * 0
-        w_term = 0.01
+    # positive pairs: local (a rank owns both members of its pairs); the global mean is the mean of the per-rank means
+    # (equal shard sizes).  A single token row has no temporal differences: the term is dropped (the reference's mean
+    # over an empty tensor would be NaN).
+    w_term = 0.01 if kind == "av" else patch_sparsity_weight
+    if kind == "av" and Nq <= 1:
+        term, dq_pp, dv_pp, dT_pp = (torch.zeros((), dtype=torch.float64, device=dev), torch.zeros_like(q_local),
+                                     torch.zeros_like(v_local), torch.zeros((), dtype=torch.float64, device=dev))
     else:
-        term = R.patch_sparsity(diag, patch_sparsity_threshold)
-        w_term = patch_sparsity_weight
-    (term.float() * (w_term / W)).backward()
+        term, dq_pp, dv_pp, dT_pp = k.pospair(q_local, v_local, T, kind, patch_sparsity_threshold)
     # values are global (all-reduced); the temperature gradient stays this rank's SHARE (see sharded_contrastive_step)
-    dT = 0.15 * dT_nn.double() + Tl.grad.double()
-    scal = torch.stack([s2.double() / numel, term.detach().double() / W, dT])
+    dT = 0.15 * dT_nn.double() + (w_term / W) * dT_pp.double()
+    scal = torch.stack([s2.double() / numel, term.double() / W, dT])
     if W > 1:
         dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=group)
     l_nonneg, l_term, dT_global = scal[0], scal[1], scal[2]
@@ -231,8 +238,8 @@ def sharded_regularizer_step(q_local: torch.Tensor, v_local: torch.Tensor, tempe
         dT = dT - 40.0 * neg_log / Td / W              # every rank carries 1/W of it, so the shares still add up
         dT_global = dT_global - 40.0 * neg_log / Td
     out = {"reg": reg.to(torch.float32), "dT": dT.to(torch.float32), "dT_global": dT_global.to(torch.float32),
-           "dq": (0.15 * dq_nn.float() + ql.grad.float()).to(q_local.dtype),
-           "dv": (0.15 * dv_nn.float() + vl.grad.float()).to(v_local.dtype)}
+           "dq": (0.15 * dq_nn.float() + (w_term / W) * dq_pp.float()).to(q_local.dtype),
+           "dv": (0.15 * dv_nn.float() + (w_term / W) * dv_pp.float()).to(v_local.dtype)}
     if kind == "av":
         out["smooth"] = (0.01 * l_term).to(torch.float32)
     return out

@@ -240,8 +240,7 @@ class TriadSimilarityMixin:
         from . import regularizers as R
         tok = token_sims
         l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -60.0)
-        diag = R.positive_pair_token_sims(tok.q, tok.v, self.temperature)
-        l_smooth = R.temporal_smoothness(diag)
+        l_smooth = R.temporal_smoothness(tok.q, tok.v, self.temperature)
         if l_cal is None:
             l_cal = self._temperature_calibration()
         reg = l_cal + 0.15 * l_nonneg + 0.01 * l_smooth
@@ -252,8 +251,7 @@ class TriadSimilarityMixin:
         from . import regularizers as R
         tok = token_sims
         l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -20.0)
-        diag = R.positive_pair_token_sims(tok.q, tok.v, self.temperature)
-        sparsity = R.patch_sparsity(diag, self.patch_sparsity_threshold)
+        sparsity = R.patch_sparsity(tok.q, tok.v, self.temperature, self.patch_sparsity_threshold)
         return 0.15 * l_nonneg + self.patch_sparsity_weight * sparsity
 
     def compute_contrastive_loss_av(self, clip_sims, token_sims):

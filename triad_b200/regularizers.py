@@ -13,8 +13,10 @@ Two kinds of term read the token-similarity tensor the fused path never builds:
   GEMMs.  Nothing of size B^2*Nq*Nv is ever resident (see DESIGN.md §4 K5 for why the two backward
   GEMMs are not fused into a flash-attention-style kernel at D = 512).
 * terms on the B POSITIVE pairs only (token_sims[i,i]): temporal smoothness (model.py:394-408)
-  and patch-usage sparsity (:528-541).  They touch B*Nq*Nv elements — 1/B of the tensor — and are
-  written with the reference's own ATen ops on a batched GEMM of the diagonal blocks.
+  and patch-usage sparsity (:528-541).  They touch B*Nq*Nv elements — 1/B of the tensor:
+  ``PositivePairTerm`` = one small batched library GEMM of the diagonal blocks, ONE kernel
+  (``triad_pospair_terms``: value, d value / d<q,v> and d value / dT in a single pass) and two small
+  batched GEMMs in backward, instead of the ~40 ATen kernels of the reference's autograd graph.
 """
 from __future__ import annotations
 
@@ -23,9 +25,17 @@ import torch
 from . import _lib, ops
 from ._lib import check
 
-#: bytes of one raw-similarity chunk (rows x images-in-chunk x Nv).  2 GiB: the three GEMMs stay large and the
-#: fp32 accumulation of dQ across chunks (one extra pass over dQ per chunk) is paid 4x at the B=256 shape
-CHUNK_BYTES = 2 << 30
+#: upper bound on the bytes of one chunk of N = dL/d<q,v> (rows x images-in-chunk x Nv, bf16/fp32).  When the whole
+#: batch fits (cfg 2: 8.4 GB, cfg 3: 10.3 GB of the 180 GB) there is ONE chunk: dQ = N V is a single GEMM with the
+#: contraction over all images (fp32 accumulation inside the GEMM, one rounding), and nothing is accumulated across
+#: chunks.  Larger batches fall back to several chunks with an fp32 dQ accumulator.  The budget is also capped at a
+#: quarter of the memory that is free at the time of the call (chunk_budget).
+CHUNK_BYTES = 16 << 30
+
+
+def chunk_budget(device, chunk_bytes: int) -> int:
+    free, _ = torch.cuda.mem_get_info(device)
+    return max(1 << 20, min(int(chunk_bytes), free // 4)) if chunk_bytes >= (1 << 20) else int(chunk_bytes)
 
 
 def nonneg_chunk(S: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write_grad: bool,
@@ -76,7 +86,8 @@ def nonneg_fused_chunk(q: torch.Tensor, vc: torch.Tensor, T: torch.Tensor, lo: f
 def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, numel: float, need_grads: bool,
                  chunk_bytes: int):
     """One sweep over image chunks.  Returns (sums fp64 [2] = {sum clamp^2, dl/dT for l = sum clamp^2 / numel},
-    dq fp32 [Bq*Nq, D] or None, dv [Bv,Nv,D] in the input dtype or None); the gradients are those of
+    dq [Bq*Nq, D] (input dtype when one chunk held all images, else the fp32 accumulator) or None, dv [Bv,Nv,D] in
+    the input dtype or None); the gradients are those of
     sum clamp(T<q,v>, lo, 0)^2 / numel.  `numel` is the caller's normaliser (all pairs of the GLOBAL batch when the
     rows are one rank's shard)."""
     q, v = q.contiguous(), v.contiguous()
@@ -89,8 +100,9 @@ def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, n
     M = Bq * Nq
     q2 = q.view(M, D)
     sums = torch.zeros(2, dtype=torch.float64, device=q.device)
-    jc = max(1, min(Bv, int(chunk_bytes) // max(1, M * Nv * q.element_size())))
-    dq32 = torch.zeros(M, D, dtype=torch.float32, device=q.device) if need_grads else None
+    jc = max(1, min(Bv, chunk_budget(q.device, chunk_bytes) // max(1, M * Nv * q.element_size())))
+    single = jc >= Bv                                        # one chunk: dQ = N V in one GEMM, no accumulator
+    dq = torch.zeros(M, D, dtype=torch.float32, device=q.device) if (need_grads and not single) else None
     dv = torch.empty_like(v) if need_grads else None
     for j0 in range(0, Bv, jc):
         vc = v[j0:j0 + jc].reshape(-1, D)
@@ -100,11 +112,29 @@ def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, n
             S = torch.mm(q2, vc.t())                        # raw <q,v>, rounded to the input dtype like the reference's matmul
             nonneg_chunk(S, T, lo, 2.0 / numel, need_grads, sums)  # in place: S -> N = dl_nonneg/d<q,v>
         if need_grads:
-            dq32.add_(torch.mm(S, vc))
-            dv[j0:j0 + jc] = torch.mm(S.t(), q2).view(-1, Nv, D)
+            if single:
+                dq = torch.mm(S, vc)
+            else:
+                dq.add_(torch.mm(S, vc))
+            torch.mm(S.t(), q2, out=dv[j0:j0 + jc].view(-1, D))
     if dv is not None and Nv != Nv_true:
         dv = dv[:, :Nv_true].contiguous()
-    return sums, dq32, dv
+    return sums, dq, dv
+
+
+def scale_by(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """x * s for a 0-dim DEVICE scalar s (the upstream gradient inside backward).  torch's broadcast of a 0-dim CUDA
+    tensor takes the strided TensorIterator path (0.87 TB/s on a 65 MB gradient); this is one vectorised stream."""
+    lib = _lib.load()
+    x = x.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        return x * s.to(x.dtype)
+    s32 = s.detach().to(device=x.device, dtype=torch.float32).reshape(())
+    y = torch.empty_like(x)
+    with ops._on(x):
+        check(lib.triad_scale(x.data_ptr(), y.data_ptr(), x.numel(), ops._dtype_code(x), s32.data_ptr(),
+                              ops._stream(x.device)), "triad_scale")
+    return y
 
 
 class DenseNonNeg(torch.autograd.Function):
@@ -137,8 +167,8 @@ class DenseNonNeg(torch.autograd.Function):
         if not ctx.need:
             return None, None, None, None, None
         dq, dv, dT = ctx.saved_tensors
-        gq = dq * gl.to(dq.dtype) if ctx.needs_input_grad[0] else None
-        gv = dv * gl.to(dv.dtype) if ctx.needs_input_grad[1] else None
+        gq = scale_by(dq, gl) if ctx.needs_input_grad[0] else None
+        gv = scale_by(dv, gl) if ctx.needs_input_grad[1] else None
         gT = None
         if ctx.needs_input_grad[2] and ctx.t_shape is not None:
             gT = (dT * gl).reshape(ctx.t_shape).to(ctx.t_dtype)
@@ -151,21 +181,65 @@ def nonneg_pressure(q, v, temperature, lo: float, chunk_bytes=None) -> torch.Ten
 
 def positive_pair_token_sims(q, v, temperature) -> torch.Tensor:
     """token_sims[i,i] for every i: (B,Nq,Nv) = T * q_i v_i^T — the diagonal blocks the reference stacks
-    at model.py:405 / :528-534 (same rounding: matmul output in the input dtype, then * T)."""
+    at model.py:405 / :528-534 (same rounding: matmul output in the input dtype, then * T).  Inspection aid; the loss
+    path uses PositivePairTerm."""
     if q.shape[0] != v.shape[0]:
         raise ValueError("the positive-pair regularisers need as many queries as images")
     return torch.bmm(q, v.transpose(1, 2)) * temperature
 
 
-def temporal_smoothness(diag: torch.Tensor) -> torch.Tensor:
+SMOOTHNESS, SPARSITY = 0, 1
+
+
+class PositivePairTerm(torch.autograd.Function):
+    """Temporal smoothness (mode SMOOTHNESS, model.py:394-408) or patch-usage sparsity (mode SPARSITY,
+    model.py:528-541) of the positive pairs, with dq, dv, dT.  Forward: one batched library GEMM of the diagonal
+    blocks (raw <q_i, v_i>, rounded to the input dtype like the reference's matmul) and triad_pospair_terms, which
+    returns the value together with G = d value / d raw and d value / dT; backward: dq_i = G_i v_i, dv_i = G_i^T q_i."""
+
+    @staticmethod
+    def forward(ctx, q, v, temperature, mode, threshold):
+        ops._require_cuda(q, v)
+        if q.dtype != v.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("PositivePairTerm supports float32 and bfloat16 embeddings of one dtype")
+        if q.shape[0] != v.shape[0]:
+            raise ValueError("the positive-pair regularisers need as many queries as images")
+        lib = _lib.load()
+        q, v = q.contiguous(), v.contiguous()
+        B, Nq, _ = q.shape
+        Nv = v.shape[1]
+        T = ops.temperature_tensor(temperature, q.device)
+        raw = torch.bmm(q, v.transpose(1, 2))
+        G = torch.empty_like(raw)
+        sums = torch.empty(2, dtype=torch.float64, device=q.device)
+        with ops._on(q):
+            ws = ops._Workspace.get(lib.triad_pospair_workspace_bytes(B), q.device, "pospair")
+            check(lib.triad_pospair_terms(raw.data_ptr(), ops._dtype_code(raw), T.data_ptr(), int(mode), float(threshold),
+                                          B, Nq, Nv, G.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          ops._stream(q.device)), "triad_pospair_terms")
+        ctx.save_for_backward(q, v, G, sums)
+        ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
+        ctx.t_dtype = temperature.dtype if isinstance(temperature, torch.Tensor) else None
+        return sums[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gl):
+        q, v, G, sums = ctx.saved_tensors
+        Gs = scale_by(G, gl) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
+        gq = torch.bmm(Gs, v) if ctx.needs_input_grad[0] else None
+        gv = torch.bmm(Gs.transpose(1, 2), q) if ctx.needs_input_grad[1] else None
+        gT = None
+        if ctx.needs_input_grad[2] and ctx.t_shape is not None:
+            gT = (sums[1].to(torch.float32) * gl).reshape(ctx.t_shape).to(ctx.t_dtype)
+        return gq, gv, gT, None, None
+
+
+def temporal_smoothness(q, v, temperature) -> torch.Tensor:
     """model.py:394-408 on the diagonal blocks."""
-    d = diag[:, 1:] - diag[:, :-1]
-    return torch.mean(d ** 2)
+    return PositivePairTerm.apply(q, v, temperature, SMOOTHNESS, 0.0)
 
 
-def patch_sparsity(diag: torch.Tensor, threshold: float) -> torch.Tensor:
+def patch_sparsity(q, v, temperature, threshold: float) -> torch.Tensor:
     """model.py:536-541: softmax over patches, usage fraction per patch (padded tokens included, as in the
     reference), squared excess over the threshold."""
-    probs = torch.softmax(diag, dim=-1)
-    frac = probs.sum(dim=1) / probs.shape[1]
-    return (torch.relu(frac - threshold) ** 2).mean()
+    return PositivePairTerm.apply(q, v, temperature, SPARSITY, float(threshold))
