@@ -184,6 +184,18 @@ int triad_nonneg_fused_chunk(const void* q, const void* v, const float* temperat
                              void* n_out, long long ldn, int write_grad, double* sums,
                              void* ws, size_t ws_bytes, void* stream);
 
+/* The max-mean forward (triad_maxmean_fwd: clip, idx) AND the dense regulariser's N = dL/d<q,v> (as
+ * triad_nonneg_fused_chunk with write_grad = 1, all Bv images in one call; sums[0..1] accumulated) from ONE pass over
+ * the similarities: the training step with the reference's full loss (model.py:430-472 calls both on the same
+ * token_sims) needs both of every tile.  bf16, D % 64 == 0, D <= 512, Nv <= 256, Nv % 8 == 0, all rows (padded text
+ * tokens take part in the regulariser, model.py:525, so rows are not packed).  flags: TRIAD_FWD_FORCE_1CTA,
+ * TRIAD_FWD_SYNC_CHUNKS. */
+size_t triad_maxmean_fwd_nonneg_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D);
+int triad_maxmean_fwd_nonneg(const void* q, const void* v, const float* row_scale, const float* temperature,
+                             int Bq, int Bv, int Nq, int Nv, int D, float* clip, void* idx,
+                             float lo, float coef, void* n_out, long long ldn, double* sums,
+                             void* ws, size_t ws_bytes, int flags, void* stream);
+
 /* Regularisers on the B POSITIVE pairs only (token_sims[i,i]): temporal smoothness (mode 0, model.py:394-408:
  * mean over (i, a < Nq-1, p) of (S[i,a+1,p] - S[i,a,p])^2) and patch-usage sparsity (mode 1, model.py:528-541:
  * softmax over patches, usage fraction per patch over ALL Nq token rows, mean of relu(frac - threshold)^2).

@@ -48,8 +48,8 @@ def main():
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     # the last full step: from the last-but-one forward kernel to the last one
-    # (the contrastive forward only: the dense-regulariser passes are the same kernel with kEmitN = true)
-    fw = [k for k, e in enumerate(evs) if re.search(r"maxmean_tc_kernel<\d, (false|true), false>", e.name)]
+    # (the max-mean forward, kMode 0 or 2; a regulariser-only pass is the same kernel with kMode 1)
+    fw = [k for k, e in enumerate(evs) if re.search(r"maxmean_tc_kernel<\d, (false|true), [02]>", e.name)]
     a, b = fw[-2], fw[-1]
     t0 = evs[a].time_range.start
     prev_end = None

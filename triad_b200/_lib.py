@@ -53,6 +53,10 @@ SIGNATURES = {
     "triad_nonneg_fused_workspace_bytes": (c_size_t, []),
     "triad_nonneg_fused_chunk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                          c_void_p, ctypes.c_longlong, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "triad_maxmean_fwd_nonneg_workspace_bytes": (c_size_t, [c_int] * 5),
+    "triad_maxmean_fwd_nonneg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p, c_float, c_float, c_void_p, ctypes.c_longlong, c_void_p,
+                                         c_void_p, c_size_t, c_int, c_void_p]),
     "triad_pospair_workspace_bytes": (c_size_t, [c_int]),
     "triad_pospair_terms": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),

@@ -141,6 +141,51 @@ extern "C" int triad_maxmean_fwd(const void* q, const void* v, const float* row_
                     ws, ws_bytes, flags, (cudaStream_t)stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// max-mean forward + dense non-negative-pressure regulariser from ONE pass over the similarities (bf16, tcgen05)
+// workspace: [0,256) control | max-mean partial sums | regulariser partials
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t triad_maxmean_fwd_nonneg_workspace_bytes(int Bq, int Bv, int Nq, int Nv, int D) {
+    (void)Nv; (void)D;
+    if (Bq <= 0 || Bv <= 0 || Nq <= 0) return 0;
+    return 256 + fwd_part_bytes(Bq * Nq, Bv, Nq) + (size_t)kNonnegFusedPartials * 2 * sizeof(double);
+}
+
+extern "C" int triad_maxmean_fwd_nonneg(const void* q, const void* v, const float* row_scale, const float* temperature,
+                                        int Bq, int Bv, int Nq, int Nv, int D, float* clip, void* idx,
+                                        float lo, float coef, void* n_out, long long ldn, double* sums,
+                                        void* ws, size_t ws_bytes, int flags, void* stream) {
+    if (!q || !v || !row_scale || !temperature || !clip || !idx || !n_out || !sums || !ws)
+        return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_fwd_nonneg: null pointer");
+    if (Bq <= 0 || Bv <= 0 || Nq <= 0 || Nv <= 0 || D <= 0) return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_fwd_nonneg: bad shape");
+    if ((long long)Bq * Nq > 0x7fffffffLL) return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_fwd_nonneg: Bq*Nq overflows int32");
+    if (!tc_supported(Nv, D) || Nv > 256 || Nv % 8 != 0)
+        return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_fwd_nonneg: needs D % 64 == 0, D <= 512, Nv <= 256, Nv % 8 == 0");
+    if (!(lo < 0.f)) return fail_msg(TRIAD_ERR_BAD_ARG, "maxmean_fwd_nonneg: lo must be negative");
+    if (ldn < (long long)Bv * Nv || ldn % 8 != 0 || (long long)ldn * 2 >= (1ll << 40)) return fail_msg(TRIAD_ERR_BAD_SHAPE, "maxmean_fwd_nonneg: ldn");
+    if (((uintptr_t)q | (uintptr_t)v | (uintptr_t)n_out | (uintptr_t)ws) & 15) return fail_msg(TRIAD_ERR_ALIGNMENT, "maxmean_fwd_nonneg: 16-byte alignment");
+    if (ws_bytes < triad_maxmean_fwd_nonneg_workspace_bytes(Bq, Bv, Nq, Nv, D)) return fail_msg(TRIAD_ERR_WORKSPACE, "maxmean_fwd_nonneg: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    TRIAD_CUDA_CHECK(cudaGetDevice(&dev));
+    TRIAD_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sms * 8 > kNonnegFusedPartials) return fail_msg(TRIAD_ERR_UNSUPPORTED, "maxmean_fwd_nonneg: too many SMs for the partial buffer");
+    const int M = Bq * Nq;
+    int* abort_flag = (int*)ws;
+    float* part = (float*)((char*)ws + 256);
+    double* npart = (double*)((char*)ws + 256 + fwd_part_bytes(M, Bv, Nq));
+    TRIAD_CUDA_CHECK(cudaMemsetAsync(abort_flag, 0, 256, st));
+    EmitNArgs e{n_out, ldn, lo, coef, 1, npart, 1};
+    const int cta_group = (flags & TRIAD_FWD_FORCE_1CTA) ? 1 : 2;
+    int rc = launch_maxmean_tc(q, v, row_scale, temperature, 0, M, Bv, Nq, Nv, D, part, idx, abort_flag, cta_group, flags,
+                               nullptr, &e, st);
+    if (rc) return rc;
+    rc = launch_nonneg_finish(npart, sms * 8, sums, st);
+    if (rc) return rc;
+    if (flags & TRIAD_FWD_TEST_TRIP_WATCHDOG) TRIAD_CUDA_CHECK(cudaMemsetAsync(abort_flag, 1, 4, st));
+    return launch_finalize_clip(part, Bq, Bv, Nq, clip, abort_flag, st);
+}
+
 // Synchronises `stream` and reports whether the forward kernel that last used `ws` hit its
 // deadlock watchdog (debug / test aid; the hot path never calls it).
 extern "C" int triad_maxmean_fwd_status(const void* ws, void* stream) {

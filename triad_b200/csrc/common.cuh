@@ -86,13 +86,17 @@ int launch_row_scale(const int64_t* mask, int Bq, int Nq, float* row_scale, cuda
 int launch_maxmean_simt(const void* q, const void* v, const float* row_scale, const float* T,
                         int inv_T, int M, int Bv, int Nq, int Nv, int D, int dtype,
                         float* part, void* idx, cudaStream_t st);   // idx: [Bv][M/Nq][nq_padded(Nq)]
-// dense-regulariser mode of the tcgen05 forward (maxmean_tc.cu, kEmitN): instead of reducing each tile the
-// epilogue writes N = dL/d<q,v> of the non-negative-pressure term; partials: [SMs*8][2] doubles
-struct EmitNArgs { void* n_out; long long ldn; float lo, coef; int write_n; double* partials; };
+// dense-regulariser modes of the tcgen05 forward (maxmean_tc.cu, kMode): the epilogue writes N = dL/d<q,v> of the
+// non-negative-pressure term — instead of reducing each tile (with_maxmean = 0) or next to the max-mean reduction
+// (with_maxmean = 1: clip partials, idx and N from ONE pass over the similarities); partials: [SMs*8][2] doubles
+struct EmitNArgs { void* n_out; long long ldn; float lo, coef; int write_n; double* partials; int with_maxmean; };
 int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, const float* T,
                       int inv_T, int M, int Bv, int Nq, int Nv, int D,
                       float* part, void* idx, int* abort_flag, int cta_group, int flags, const int* pack_maps,
                       const EmitNArgs* emit, cudaStream_t st);
+// sums[0..1] += the per-warp partials of a dense-regulariser forward, in slot order (dense_reg.cu)
+constexpr int kNonnegFusedPartials = 4096;                      // >= SMs * 8 epilogue warps
+int launch_nonneg_finish(const double* partials, int n, double* sums, cudaStream_t st);
 int launch_finalize_clip(const float* part, int Bq, int Bv, int Nq, float* clip, const int* abort_flag, cudaStream_t st);
 // packed rows (pack.cu): maps = off[Bq+1] | rowmap[Bq*Nq] | scratch
 size_t pack_map_bytes(int Bq, int Nq);

@@ -119,71 +119,111 @@ __device__ __forceinline__ void first_ge32(const uint32_t (&r)[32], int col0, in
     if (lo < min(lim, 32)) best = col0 + lo;            // 64 = "none"; columns >= lim are padding
 }
 
-// dense-regulariser epilogue, one 32-column chunk of the warp's 32 rows: o = coefT*min(T*acc, 0) as bf16, sum of
-// min(.)^2 and the row minimum (to detect the clamp floor) in four independent chains.  A thread owns a ROW of
-// the accumulator, so storing straight from registers would hit 32 different rows per store instruction (32
-// half-filled sectors); the 32 x 64-byte block is instead transposed through a small shared-memory staging area
-// (16 columns at a time, row pitch 48 bytes: conflict-free for both phases) and leaves as 16 rows x one full
-// 32-byte sector per instruction.
-// Columns >= Nv contribute nothing and are not stored (Nv % 8 == 0: whole 16-byte pieces).
-constexpr uint32_t kStgPitch = 48;                                  // bytes per staged row (16 columns = 32 bytes, + 16)
-constexpr uint32_t kStgBytesPerWarp = 32 * kStgPitch;               // 1536 (8 epilogue warps: 12 KB, inside one ring stage)
+// ---- dense-regulariser epilogue (kMode 1: instead of the max-mean reduction; kMode 2: next to it) -----------------
+// N = coef*T*min(T*acc, 0) = (coef*T^2) * min(acc, 0) for T > 0, written as bf16.  A thread owns a ROW of the
+// accumulator, so storing straight from registers would hit 32 different rows per store instruction.  Each epilogue
+// warp instead stages a 32-row x 64-column box (4 KB, the SWIZZLE_128B layout of a TMA box: 16-byte piece c of row
+// r sits at piece c ^ (r & 7), so the 32 lanes' st.shared.v4 are conflict-free) and ONE lane hands it to the TMA
+// unit (cp.async.bulk.tensor store): no per-lane global stores, no address arithmetic, and rows >= M / columns >= Nv
+// are clipped by the tensor map {Nv, images, M}.  Round 1's version (per-lane 16-byte stores out of a transposing
+// staging buffer) spent 4 dependent STS -> LDS -> STG round trips per chunk: 3.8 ms per pass against 2.45 ms for
+// the plain forward.
 constexpr int kEmitEpiWarps = 8;                                    // two per scheduler: columns [0,128) and [128,256)
 constexpr int kEmitThreads = (kEpiWarp0 + kEmitEpiWarps) * 32;      // 384
+constexpr uint32_t kStgBytesPerWarp = 32 * 128;                     // one 32 x 64 bf16 box
+constexpr uint32_t kStgBytes = kEmitEpiWarps * kStgBytesPerWarp;    // 32 KB, carved from the end of the V ring
 constexpr uint16_t kNoCol = 0xffffu;                                // "no column of my half reaches the threshold"
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 u;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
-    return u;
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<unsigned long long&>(acc))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(r))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return r;
 }
 
+// One 32-column chunk of the warp's 32 rows, fast path: n = min(acc, 0); a2 += n^2 (two packed chains; the tile's sum
+// is scaled by T^2 afterwards); mn = row minimum (to detect the clamp floor); bf16(n * cT2) into the staging box
+// (`sub` = which 64-byte half of the 128-byte staged row).  Columns >= Nv (stale TMEM beyond n_umma) are zeroed in
+// the last, partial chunk only (kFull = false).
 template <bool kFull>
-__device__ __forceinline__ void emit_chunk_fast_t(const uint32_t (&r)[32], int col0, int Nv, float Tval, float coefT,
-                                                  float (&a2)[4], float (&mn)[4], bool store, uint32_t stg, int lane,
-                                                  __nv_bfloat16* nblock /* &N[warp's first row][image's first column] */,
-                                                  long long ldn, int rows_valid) {
-    uint32_t packed[16];
+__device__ __forceinline__ void emit_chunk_t(const uint32_t (&r)[32], int col0, int Nv, float2 cT2, float2 (&a2)[2],
+                                             float (&mn)[2], uint32_t (&w)[16]) {
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
-        float s0 = __uint_as_float(r[e]) * Tval, s1 = __uint_as_float(r[e + 1]) * Tval;
-        if constexpr (!kFull) { if (col0 + e >= Nv) s0 = 0.f; if (col0 + e + 1 >= Nv) s1 = 0.f; }
-        const float n0 = fminf(s0, 0.f), n1 = fminf(s1, 0.f);
-        const int k = (e >> 1) & 3;
-        a2[k] = fmaf(n0, n0, a2[k]);
-        a2[k] = fmaf(n1, n1, a2[k]);
-        mn[k] = fminf(mn[k], fminf(s0, s1));
-        __nv_bfloat162 hh = __floats2bfloat162_rn(n0 * coefT, n1 * coefT);
-        packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-    }
-    if (!store) return;                                             // warp-uniform (write_n)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {                                   // two 16-column halves of the chunk
-        sts128(stg + lane * kStgPitch, packed[8 * h], packed[8 * h + 1], packed[8 * h + 2], packed[8 * h + 3]);
-        sts128(stg + lane * kStgPitch + 16, packed[8 * h + 4], packed[8 * h + 5], packed[8 * h + 6], packed[8 * h + 7]);
-        __syncwarp();
-        const int piece = lane & 1;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int row = 16 * i + (lane >> 1);
-            const uint4 u = lds128(stg + row * kStgPitch + 16 * piece);
-            const int col = col0 + 16 * h + 8 * piece;
-            // streaming store: N (gigabytes per call) must not evict the V chunk and the query tiles from L2
-            if (row < rows_valid && col < Nv) __stcs(reinterpret_cast<uint4*>(nblock + (size_t)row * (size_t)ldn + col), u);
-        }
-        __syncwarp();
+        float x0 = __uint_as_float(r[e]), x1 = __uint_as_float(r[e + 1]);
+        if constexpr (!kFull) { if (col0 + e >= Nv) x0 = 0.f; if (col0 + e + 1 >= Nv) x1 = 0.f; }
+        const float2 n = make_float2(fminf(x0, 0.f), fminf(x1, 0.f));
+        ffma2(a2[(e >> 1) & 1], n, n);
+        mn[(e >> 1) & 1] = fmin3(mn[(e >> 1) & 1], n.x, n.y);
+        const float2 o = fmul2(n, cT2);
+        __nv_bfloat162 hh = __floats2bfloat162_rn(o.x, o.y);
+        w[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
     }
 }
-// the per-column mask of the last, partial chunk costs an ISETP + FSEL per element: only that chunk pays for it
-__device__ __forceinline__ void emit_chunk_fast(const uint32_t (&r)[32], int col0, int Nv, float Tval, float coefT,
-                                                float (&a2)[4], float (&mn)[4], bool store, uint32_t stg, int lane,
-                                                __nv_bfloat16* nblock, long long ldn, int rows_valid) {
-    if (col0 >= Nv) return;                                         // warp-uniform
-    if (col0 + 32 <= Nv) emit_chunk_fast_t<true>(r, col0, Nv, Tval, coefT, a2, mn, store, stg, lane, nblock, ldn, rows_valid);
-    else emit_chunk_fast_t<false>(r, col0, Nv, Tval, coefT, a2, mn, store, stg, lane, nblock, ldn, rows_valid);
+__device__ __forceinline__ void emit_chunk(const uint32_t (&r)[32], int col0, int Nv, float2 cT2, float2 (&a2)[2],
+                                           float (&mn)[2], uint32_t (&w)[16]) {
+    if (col0 >= Nv) return;                                         // warp-uniform; the staged half is clipped by TMA
+    if (col0 + 32 <= Nv) emit_chunk_t<true>(r, col0, Nv, cT2, a2, mn, w);
+    else emit_chunk_t<false>(r, col0, Nv, cT2, a2, mn, w);
+}
+// the chunk's 32 bf16 (64 bytes) of this lane's row into the staging box; `sub` = which half of the 128-byte row
+__device__ __forceinline__ void stage_chunk(const uint32_t (&w)[16], uint32_t stg_row, int lane, int sub) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        sts128(stg_row + ((uint32_t)((sub * 4 + g) ^ (lane & 7)) << 4), w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+}
+// Exact variant of one chunk (some similarity of the warp's rows is at the clamp floor `lo`): near the floor the
+// reference's own rounding decides the gradient gate — token_sims is bf16(bf16(<q,v>) * T) under autocast
+// (model.py:387), clamp and its gradient act on that.  e2 += clamp(S,lo,0)^2, eT += dS * <q,v> (both unscaled by coef).
+__device__ __forceinline__ void emit_chunk_exact(const uint32_t (&r)[32], int col0, int Nv, float Tval, float coefT, float lo,
+                                                 float& e2, float& eT, uint32_t (&w)[16]) {
+    if (col0 >= Nv) return;
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+        float o[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float raw = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[e + h])));
+            const float sv = (col0 + e + h < Nv) ? __bfloat162float(__float2bfloat16_rn(raw * Tval)) : 0.f;
+            const float n = fminf(sv, 0.f);
+            const float nc = fmaxf(n, lo);
+            e2 = fmaf(nc, nc, e2);
+            const float pass = (sv >= lo) ? n : 0.f;
+            eT = fmaf(pass, raw, eT);
+            o[h] = pass * coefT;
+        }
+        __nv_bfloat162 hh = __floats2bfloat162_rn(o[0], o[1]);
+        w[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+}
+// the staged box -> N[row0 .. row0+32)[image j][col0 .. col0+64): the writes of all 32 lanes are made visible to the
+// async proxy, then one lane issues the bulk tensor store and commits it as a bulk group
+__device__ __forceinline__ void emit_box_store(const CUtensorMap* tmap_n, uint32_t stg, int col0, int j, int row0, int lane) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tmap_n)), "r"(stg), "r"(col0), "r"(j), "r"(row0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+// before the staging box is written again: the TMA unit must have READ the previous one
+__device__ __forceinline__ void emit_box_reusable(int lane) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
+// all of this warp's bulk stores have been performed (before generic stores to the same addresses / kernel exit)
+__device__ __forceinline__ void emit_box_drain(int lane) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
 }
 
 struct Tile { int m, j; };
@@ -249,13 +289,17 @@ struct TileIter {
 // ---------------------------------------------------------------------------------------------
 // kSub = false: one accumulator tile per image (Nv <= 256), the training shapes' hot path;
 // kSub = true : n_sub 256-patch sub-tiles per image.
-template <int kCtaGroup, bool kSub, bool kEmitN = false>
+// kMode 0: max-mean reduction (the contrastive forward / retrieval); 1: dense-regulariser pass only (the epilogue
+// writes N = dL/d<q,v> of the non-negative pressure term); 2: BOTH in one pass over the similarities — the training
+// step with the reference's full loss needs the max-mean reduction and N of the very same tiles.
+template <int kCtaGroup, bool kSub, int kMode = 0>
 __global__ void __launch_bounds__(kEmitThreads, 1)
 maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_v,
-                  const Params p) {
+                  const __grid_constant__ CUtensorMap tmap_n, const Params p) {
+    constexpr bool kEmitN = kMode != 0;
     constexpr int kVStageBytes = (kMaxN / kCtaGroup) * kBlockK * 2;       // 32 KB / 16 KB
-    // dense-regulariser mode gives the last ring stage (>= 16 KB) to the epilogue's store staging (4 x 2560 B)
-    constexpr int kStages = kVRingBytes / kVStageBytes - (kEmitN ? 1 : 0);   // 3 / 6  (2 / 5)
+    // the dense-regulariser modes give the last 32 KB of the ring to the epilogue's store staging (8 warps x 4 KB)
+    constexpr int kStages = (kVRingBytes - (kEmitN ? kStgBytes : 0)) / kVStageBytes;   // 3 / 6  (2 / 4)
     constexpr int kTileRows = kBlockM * kCtaGroup;
 
     extern __shared__ uint8_t smem_raw[];
@@ -403,31 +447,31 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 prev_m = t.m;
             }
         }
-    } else if (warp >= kEpiWarp0 && kEmitN) {
+    } else if (warp >= kEpiWarp0 && kMode == 1) {
         // ============ epilogue, dense-regulariser mode: N = coef*T*min(S,0) for every pair =============
-        // One pass over the accumulator: s = T*acc, n = min(s, 0); the tile's sum of n^2 feeds the value and,
+        // One pass over the accumulator: n = min(acc, 0); the tile's sum of n^2 (times T^2) feeds the value and,
         // because n*s == n^2, also dL/dT (sum dS*<q,v> = sum n^2 / T).  The clamp floor `lo` (-60 / -20) is far
         // outside the data range; a tile that does come near it (row minimum within two bf16 ulps of lo) is redone
-        // with the reference's bf16 rounding of S, clamp and gradient gate before its accumulator is released.  Padded text tokens take part, as in the reference (model.py:525).
+        // with the reference's bf16 rounding of S, clamp and gradient gate before its accumulator is released.
+        // Padded text tokens take part, as in the reference (model.py:525).
         const int quarter = warp & 3;
         const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
         const float Tval = *p.T;
         const float coefT = p.coef * Tval;
+        const float2 cT2 = make_float2(coefT * Tval, coefT * Tval);
+        const double Td = (double)Tval, T2d = (double)Tval * (double)Tval;
         const int half = (warp - kEpiWarp0) >> 2;                  // 0: columns [0,128), 1: [128,256)
         const uint32_t stg = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0) * kStgBytesPerWarp;
+        const uint32_t stg_row = stg + (uint32_t)lane * 128u;
+        const bool wn = p.write_n != 0;
         double s2 = 0.0, sT = 0.0;
         uint32_t t_cnt = 0;
         bool alive = true;
         Tile t;
-        constexpr int kCh = kMaxN / 32 / 2;                         // 32-column chunks per warp
-        const int cbase = half * kCh;
+        const int own = half * 4;                                   // this warp's 32-column chunks: [own, own + 4)
         while (alive && it.next(t)) {
             const int wrow0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;      // the warp's first row
-            const int r = wrow0 + lane;
-            const bool vrow = r < p.M;
-            const int rows_valid = max(0, min(32, p.M - wrow0));
-            __nv_bfloat16* nblock = p.n_out + (size_t)min(wrow0, p.M - 1) * (size_t)p.ldn + (size_t)t.j * p.Nv;
-            __nv_bfloat16* nrow = nblock + (size_t)(vrow ? lane : 0) * (size_t)p.ldn;
+            const bool vrow = wrow0 + lane < p.M;
             const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
             ++t_cnt;
             bool ok = mbar_wait(bar_t_full + 8 * acc, acc_phase, p.abort_flag, 6);
@@ -435,64 +479,50 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (!ok) { alive = false; break; }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxN;
-            // ---- fast pass: pipelined 32-column loads (chunk c+1 in flight while chunk c is processed), four
-            //      independent accumulator chains per chunk ----
-            float a2[4] = {0.f, 0.f, 0.f, 0.f}, mn[4] = {0.f, 0.f, 0.f, 0.f};
+            // ---- fast pass: pipelined 32-column loads (chunk c+1 in flight while chunk c is processed); two chunks
+            //      fill one staged box, which leaves through the TMA unit while the next two are processed ----
+            float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            float mn[2] = {0.f, 0.f};
             {
-                uint32_t bufA[32], bufB[32];
-                tmem_ld32_raw(taddr + cbase * 32, bufA);
+                uint32_t bufA[32], bufB[32], w[16];
+                tmem_ld32_raw(taddr + own * 32, bufA);
                 tmem_wait_ld();
 #pragma unroll
-                for (int cc = 0; cc < kCh; cc += 2) {
-                    const int c = cbase + cc;
+                for (int b = 0; b < 2; ++b) {
+                    const int c = own + 2 * b;
                     tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
-                    emit_chunk_fast(bufA, c * 32, p.Nv, Tval, coefT, a2, mn, p.write_n != 0, stg, lane, nblock, p.ldn, rows_valid);
+                    emit_chunk(bufA, c * 32, p.Nv, cT2, a2, mn, w);
+                    if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }   // (the previous box has been read)
                     tmem_wait_ld();
-                    if (cc + 2 < kCh) tmem_ld32_raw(taddr + (c + 2) * 32, bufA);         // compile-time condition
-                    emit_chunk_fast(bufB, (c + 1) * 32, p.Nv, Tval, coefT, a2, mn, p.write_n != 0, stg, lane, nblock, p.ldn, rows_valid);
+                    if (b == 0) tmem_ld32_raw(taddr + (c + 2) * 32, bufA);               // compile-time condition
+                    emit_chunk(bufB, (c + 1) * 32, p.Nv, cT2, a2, mn, w);
+                    if (wn) { stage_chunk(w, stg_row, lane, 1); if (c * 32 < p.Nv) emit_box_store(&tmap_n, stg, c * 32, t.j, wrow0, lane); }
                     tmem_wait_ld();
                 }
             }
-            const float a2s = (a2[0] + a2[1]) + (a2[2] + a2[3]);
-            const float mns = fminf(fminf(mn[0], mn[1]), fminf(mn[2], mn[3]));
+            const float a2s = (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
+            const float mns = fminf(mn[0], mn[1]) * Tval;
             // (margin of two bf16 ulps: the reference clamps the bf16-ROUNDED similarity, so a value a hair above
             //  the floor in fp32 can sit on it after rounding)
             if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
-                if (vrow) { s2 += (double)a2s; sT += (double)a2s / (double)Tval; }
+                if (vrow) { s2 += (double)a2s * T2d; sT += (double)a2s * Td; }
             } else {
                 // ---- exact pass (some similarity of this warp's rows is below the clamp floor): redo the tile with
                 //      the clamp and its gradient gate applied, overwriting what the fast pass stored ----
                 float e2 = 0.f, eT = 0.f;
-                for (int c = cbase; c < cbase + kCh; ++c) {
-                    if (c * 32 >= p.Nv) break;                               // warp-uniform
-                    uint32_t buf[32];
+                if (wn) emit_box_drain(lane);                               // the fast pass's stores have landed
+                for (int b = 0; b < 2; ++b) {
+                    const int c = own + 2 * b;
+                    if (c * 32 >= p.Nv) break;                              // warp-uniform
+                    uint32_t buf[32], w[16];
                     tmem_ld32_raw(taddr + c * 32, buf);
                     tmem_wait_ld();
-                    uint32_t packed[16];
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float o[2];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            // near the floor the reference's own rounding decides the gate: token_sims is
-                            // bf16(bf16(<q,v>) * T) under autocast (model.py:387), clamp and its gradient act on that
-                            const float raw = __bfloat162float(__float2bfloat16_rn(__uint_as_float(buf[e + h])));
-                            const float sv = (c * 32 + e + h < p.Nv) ? __bfloat162float(__float2bfloat16_rn(raw * Tval)) : 0.f;
-                            const float n = fminf(sv, 0.f);
-                            const float nc = fmaxf(n, p.lo);
-                            e2 = fmaf(nc, nc, e2);
-                            const float pass = (sv >= p.lo) ? n : 0.f;
-                            eT = fmaf(pass, raw, eT);
-                            o[h] = pass * coefT;
-                        }
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(o[0], o[1]);
-                        packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    if (p.write_n && vrow) {
-                        for (int k = 0; k < 4 && c * 32 + 8 * k < p.Nv; ++k)
-                            *reinterpret_cast<uint4*>(nrow + c * 32 + 8 * k) =
-                                make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
-                    }
+                    emit_chunk_exact(buf, c * 32, p.Nv, Tval, coefT, p.lo, e2, eT, w);
+                    if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
+                    tmem_ld32_raw(taddr + (c + 1) * 32, buf);
+                    tmem_wait_ld();
+                    emit_chunk_exact(buf, (c + 1) * 32, p.Nv, Tval, coefT, p.lo, e2, eT, w);
+                    if (wn) { stage_chunk(w, stg_row, lane, 1); emit_box_store(&tmap_n, stg, c * 32, t.j, wrow0, lane); }
                 }
                 if (vrow) { s2 += (double)e2; sT += (double)eT; }
             }
@@ -503,6 +533,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 else mbar_arrive_local(bar_t_empty + 8 * acc);
             }
         }
+        emit_box_reusable(lane);                                    // the staging box must outlive the last bulk read
         s2 = warp_sum_d(s2);
         sT = warp_sum_d(sT);
         if (lane == 0) {
@@ -527,6 +558,15 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         int r_orig = -1, qi = 0, piece = 0;       // original row (-1: no such row), its query, packed partial slot
         const size_t idx_pitch = (size_t)(p.M / p.Nq) * p.nq_pad;
         float R_run = 0.f; int best_run = 0;      // running (rounded max, first argmax) across the sub-tiles of an image
+        // kMode 2: this warp also emits N = dL/d<q,v> of the non-negative pressure term for ITS half of the columns
+        // (see the kMode 1 branch); T is the training-time multiplier there (inv_T == 0)
+        const float coefT = p.coef * Tval;
+        const float2 cT2 = make_float2(coefT * Tval, coefT * Tval);
+        const double Td = (double)Tval, T2d = (double)Tval * (double)Tval;
+        const uint32_t stg = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0) * kStgBytesPerWarp;
+        const uint32_t stg_row = stg + (uint32_t)lane * 128u;
+        const bool wn = kMode == 2 && p.write_n != 0;
+        double s2 = 0.0, sT = 0.0;
         bool alive = true;
         Tile t;
         while (alive && it.next(t)) {
@@ -555,7 +595,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             //      are masked by Nv — which keeps every load unconditional (see tmem_ld32_raw). ----
             constexpr int kCh = kMaxN / 32;
             float mx = -INFINITY;
-            {
+            if constexpr (kMode != 2) {
                 uint32_t bufA[32], bufB[32];
                 tmem_ld32_raw(taddr, bufA);
                 tmem_wait_ld();
@@ -567,6 +607,61 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     if (c + 2 < kCh) tmem_ld32_raw(taddr + (c + 2) * 32, bufA);          // compile-time condition
                     mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
                     tmem_wait_ld();
+                }
+            } else {
+                // ---- pass 1 + dense-regulariser emission.  Chunk order: own 0,1 | other 0,1 | own 2,3 | other 2,3
+                //      (own = this warp's half of the columns): each staged 64-column box leaves through the TMA unit
+                //      while the other half's chunks are reduced, so the staging box is free again when needed. ----
+                const int own = half * 4, oth = 4 - own;
+                float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                float mn[2] = {0.f, 0.f};
+                {
+                    uint32_t bufA[32], bufB[32], w[16];
+                    tmem_ld32_raw(taddr + own * 32, bufA);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int sq = 0; sq < 8; sq += 2) {
+                        const bool mine = (sq & 2) == 0;                                 // compile-time
+                        const int c = (mine ? own : oth) + (sq >> 2) * 2;                // chunks c, c + 1
+                        tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
+                        mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
+                        if (mine) {
+                            emit_chunk(bufA, c * 32, Nv, cT2, a2, mn, w);
+                            if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
+                        }
+                        tmem_wait_ld();
+                        if (sq + 2 < 8) tmem_ld32_raw(taddr + (((sq + 2) & 2) == 0 ? own : oth) * 32 + ((sq + 2) >> 2) * 64, bufA);
+                        mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
+                        if (mine) {
+                            emit_chunk(bufB, (c + 1) * 32, Nv, cT2, a2, mn, w);
+                            if (wn) { stage_chunk(w, stg_row, lane, 1); if (c * 32 < Nv) emit_box_store(&tmap_n, stg, c * 32, t.j, row0, lane); }
+                        }
+                        tmem_wait_ld();
+                    }
+                }
+                const bool vrow = r_orig >= 0;
+                const float a2s = (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
+                const float mns = fminf(mn[0], mn[1]) * Tval;
+                if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
+                    if (vrow) { s2 += (double)a2s * T2d; sT += (double)a2s * Td; }
+                } else {
+                    // exact pass for this warp's columns (a similarity at the clamp floor): see the kMode 1 branch
+                    float e2 = 0.f, eT = 0.f;
+                    if (wn) emit_box_drain(lane);
+                    for (int b = 0; b < 2; ++b) {
+                        const int c = own + 2 * b;
+                        if (c * 32 >= Nv) break;                                         // warp-uniform
+                        uint32_t buf[32], w[16];
+                        tmem_ld32_raw(taddr + c * 32, buf);
+                        tmem_wait_ld();
+                        emit_chunk_exact(buf, c * 32, Nv, Tval, coefT, p.lo, e2, eT, w);
+                        if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
+                        tmem_ld32_raw(taddr + (c + 1) * 32, buf);
+                        tmem_wait_ld();
+                        emit_chunk_exact(buf, (c + 1) * 32, Nv, Tval, coefT, p.lo, e2, eT, w);
+                        if (wn) { stage_chunk(w, stg_row, lane, 1); emit_box_store(&tmap_n, stg, c * 32, t.j, row0, lane); }
+                    }
+                    if (vrow) { s2 += (double)e2; sT += (double)eT; }
                 }
             }
             float R;
@@ -627,6 +722,15 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (p.pack_off == nullptr) store_group_partials(p.part, t.j, row0 >> 5, p.G, p.S, row0, p.M, p.Nq, val, lane);
             else store_group_partials_packed(p.part, t.j, p.Bq, p.pieces, qi, piece, val, lane);
         }
+        if constexpr (kMode == 2) {
+            emit_box_reusable(lane);                                // the staging box must outlive the last bulk read
+            s2 = warp_sum_d(s2);
+            sT = warp_sum_d(sT);
+            if (lane == 0) {
+                p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
+                p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
+            }
+        }
     }
 
     // ---- teardown ---------------------------------------------------------------------------
@@ -680,9 +784,10 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
     return encode_tmap_bf16(map, base, rank, dims, strides, box, true);
 }
 
-template <int kCtaGroup, bool kSub, bool kEmitN = false>
-static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& p, int n_clusters, cudaStream_t st) {
-    auto kern = maxmean_tc_kernel<kCtaGroup, kSub, kEmitN>;
+template <int kCtaGroup, bool kSub, int kMode = 0>
+static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const CUtensorMap& mn, const Params& p, int n_clusters,
+                    cudaStream_t st) {
+    auto kern = maxmean_tc_kernel<kCtaGroup, kSub, kMode>;
     TRIAD_SET_MAX_SMEM(kern, kSmemBytes);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * kCtaGroup));
@@ -696,7 +801,7 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mv, const Params& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mv, p));
+    TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mv, mn, p));
     count_launch();
     return TRIAD_OK;
 }
@@ -763,6 +868,7 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
     p.n_out = nullptr; p.ldn = 0; p.lo = 0.f; p.coef = 0.f; p.write_n = 0; p.n_partials = nullptr;
     if (emit) {
         if (n_sub > 1 || Nv % 8 != 0 || pack_maps) return fail_msg(TRIAD_ERR_UNSUPPORTED, "dense-regulariser forward: needs Nv <= 256, Nv % 8 == 0");
+        if (emit->with_maxmean && (!idx || !part || inv_T)) return fail_msg(TRIAD_ERR_BAD_ARG, "dense-regulariser + max-mean forward: needs idx and the partial buffer");
         p.n_out = (__nv_bfloat16*)emit->n_out; p.ldn = emit->ldn; p.lo = emit->lo; p.coef = emit->coef;
         p.write_n = emit->write_n; p.n_partials = emit->partials;
     }
@@ -782,16 +888,28 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
         int rc = encode_map(&mv, v, 3, dims, strides, box);
         if (rc) return rc;
     }
+    // N[row][image][patch] as a rank-3 tensor {Nv, images, M} (row pitch ldn): the epilogue's 32-row x 64-column store
+    // boxes are clipped at the image's last patch and at the last row by the TMA unit itself
+    CUtensorMap mn = mq;
+    if (emit && emit->write_n) {
+        cuuint64_t dims[3] = {(cuuint64_t)Nv, (cuuint64_t)Bv, (cuuint64_t)M};
+        cuuint64_t strides[2] = {(cuuint64_t)Nv * 2, (cuuint64_t)emit->ldn * 2};
+        cuuint32_t box[3] = {64, 1, 32};
+        int rc = encode_map(&mn, emit->n_out, 3, dims, strides, box);
+        if (rc) return rc;
+    }
     const long long total = (long long)n_m * Bv;
     if ((long long)n_clusters > total) n_clusters = (int)total;
     if (n_clusters < 1) n_clusters = 1;
     if (emit) {
-        // every CTA's four epilogue warps write a partial: clear the slots of CTAs that get no work
+        // every CTA's eight epilogue warps write a partial: clear the slots of CTAs that get no work
         TRIAD_CUDA_CHECK(cudaMemsetAsync(emit->partials, 0, (size_t)sms * kEmitEpiWarps * 2 * sizeof(double), st));
-        return cta_group == 2 ? launch_t<2, false, true>(mq, mv, p, n_clusters, st) : launch_t<1, false, true>(mq, mv, p, n_clusters, st);
+        if (emit->with_maxmean)
+            return cta_group == 2 ? launch_t<2, false, 2>(mq, mv, mn, p, n_clusters, st) : launch_t<1, false, 2>(mq, mv, mn, p, n_clusters, st);
+        return cta_group == 2 ? launch_t<2, false, 1>(mq, mv, mn, p, n_clusters, st) : launch_t<1, false, 1>(mq, mv, mn, p, n_clusters, st);
     }
-    if (n_sub > 1) return cta_group == 2 ? launch_t<2, true>(mq, mv, p, n_clusters, st) : launch_t<1, true>(mq, mv, p, n_clusters, st);
-    return cta_group == 2 ? launch_t<2, false>(mq, mv, p, n_clusters, st) : launch_t<1, false>(mq, mv, p, n_clusters, st);
+    if (n_sub > 1) return cta_group == 2 ? launch_t<2, true>(mq, mv, mn, p, n_clusters, st) : launch_t<1, true>(mq, mv, mn, p, n_clusters, st);
+    return cta_group == 2 ? launch_t<2, false>(mq, mv, mn, p, n_clusters, st) : launch_t<1, false>(mq, mv, mn, p, n_clusters, st);
 }
 
 }  // namespace triad

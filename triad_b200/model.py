@@ -42,9 +42,19 @@ class TokenSims:
         self.clip_out = clip_f32        # what compute_all_similarities_* returned as clip_sims (set by the caller)
         self.packed = False
         self.fwd_flags = 0
+        self.nonneg = None              # (N, sums, lo) when the forward also produced the dense regulariser's gradient
         self.shape = torch.Size((q.shape[0], v.shape[0], q.shape[1], v.shape[1]))
         self.dtype = q.dtype
         self.device = q.device
+
+    def take_nonneg(self, lo: float):
+        """(N, sums) of the dense regulariser if the forward produced them for this clamp floor — handed over ONCE
+        (N is gigabytes: the handle drops its reference), else None."""
+        if self.nonneg is None or self.nonneg[2] != lo:
+            return None
+        N, sums, _ = self.nonneg
+        self.nonneg = None
+        return N, sums
 
     def argmax(self) -> torch.Tensor:
         """(Bq,Bv,Nq) int64 in the reference's layout: torch.max(token_sims, dim=3)[1].
@@ -178,11 +188,25 @@ class TriadSimilarityMixin:
         # padded text tokens (weight 0, model.py:509-512) are dropped before the tensor cores
         if attention_mask is not None and q_feats.dtype == torch.bfloat16 and self.triad_pack_masked_rows:
             flags |= _lib_flags.FWD_PACK_ROWS
-        clip, idx = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale, flags,
-                                                attention_mask is None)
+        # With the reference's regularisers on, the loss call that follows needs N = dL/d<q,v> of the dense
+        # non-negative-pressure term over the very same similarity tiles (model.py:411-412 / :525-526): one pass
+        # produces both (regularizers.merged_forward_ok); all rows take part there, so no packing.
+        from . import regularizers as R
+        nonneg_lo = None
+        if (bool(getattr(self, "triad_regularizers", True)) and torch.is_grad_enabled()
+                and (q_feats.requires_grad or visual_feats.requires_grad or self.temperature.requires_grad)
+                and R.merged_forward_ok(q_feats, visual_feats)):
+            nonneg_lo = -60.0 if attention_mask is None else -20.0
+            bwd_pack = bool(flags & _lib_flags.FWD_PACK_ROWS)
+            flags &= ~_lib_flags.FWD_PACK_ROWS
+        clip, idx, N, nsums = ops.MaxMeanSimilarity.apply(q_feats, visual_feats, self.temperature, scale, flags,
+                                                          attention_mask is None, nonneg_lo,
+                                                          nonneg_lo is not None and bwd_pack)
         handle = TokenSims(q_feats, visual_feats, self.temperature, scale, attention_mask, clip, idx, prefix)
         handle.packed = bool(flags & _lib_flags.FWD_PACK_ROWS)
         handle.fwd_flags = flags
+        if N is not None:
+            handle.nonneg = (N, nsums, nonneg_lo)
         # The reference's clip_sims dtype: bf16 for AV under autocast (mean of bf16 maxima,
         # model.py:391), fp32 for TV (mask.float() promotes, model.py:509-512) and for fp32 inputs.
         out = clip.to(q_feats.dtype) if attention_mask is None else clip
@@ -239,7 +263,7 @@ class TriadSimilarityMixin:
         """compute_regularization_losses_av with the calibration term already evaluated by the fused head."""
         from . import regularizers as R
         tok = token_sims
-        l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -60.0)
+        l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -60.0, precomputed=tok.take_nonneg(-60.0))
         l_smooth = R.temporal_smoothness(tok.q, tok.v, self.temperature)
         if l_cal is None:
             l_cal = self._temperature_calibration()
@@ -250,7 +274,7 @@ class TriadSimilarityMixin:
         """reg — model.py:516-542: 0.15*mean(clamp(S,-20,0)^2) + patch_sparsity_weight*sparsity."""
         from . import regularizers as R
         tok = token_sims
-        l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -20.0)
+        l_nonneg = R.nonneg_pressure(tok.q, tok.v, self.temperature, -20.0, precomputed=tok.take_nonneg(-20.0))
         sparsity = R.patch_sparsity(tok.q, tok.v, self.temperature, self.patch_sparsity_threshold)
         return 0.15 * l_nonneg + self.patch_sparsity_weight * sparsity
 

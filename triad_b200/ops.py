@@ -142,6 +142,34 @@ def maxmean_fwd(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.
     return clip, idx
 
 
+def maxmean_fwd_nonneg(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T: torch.Tensor, lo: float, coef: float,
+                       flags: int = 0):
+    """The max-mean forward AND N = dL/d<q,v> of the dense non-negative-pressure regulariser (coef * T * clamp'(S) * S
+    for every token pair, bf16 [Bq*Nq, Bv*Nv]) from one pass over the similarities (triad_maxmean_fwd_nonneg).
+    Returns clip fp32 [Bq,Bv], idx, N, sums fp64 [2] = {sum clamp(S,lo,0)^2, sum dS*<q,v>}."""
+    lib = _lib.load()
+    _require_cuda(q, v, scale, T)
+    if q.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
+        raise TypeError("maxmean_fwd_nonneg takes bfloat16 embeddings")
+    q, v = q.contiguous(), v.contiguous()
+    Bq, Nq, D = q.shape
+    Bv, Nv, D2 = v.shape
+    if D != D2:
+        raise ValueError("embedding dims differ")
+    clip = torch.empty(Bq, Bv, dtype=torch.float32, device=q.device)
+    idx = torch.empty(Bv, Bq * nq_padded(Nq), dtype=idx_dtype(Nv), device=q.device)
+    N = torch.empty(Bq * Nq, Bv * Nv, dtype=torch.bfloat16, device=q.device)
+    sums = torch.zeros(2, dtype=torch.float64, device=q.device)
+    nws = lib.triad_maxmean_fwd_nonneg_workspace_bytes(Bq, Bv, Nq, Nv, D)
+    with _on(q):
+        ws = _Workspace.get(nws, q.device, "fwd")
+        check(lib.triad_maxmean_fwd_nonneg(q.data_ptr(), v.data_ptr(), scale.data_ptr(), T.data_ptr(), Bq, Bv, Nq, Nv, D,
+                                           clip.data_ptr(), idx.data_ptr(), float(lo), float(coef), N.data_ptr(), Bv * Nv,
+                                           sums.data_ptr(), ws.data_ptr(), ws.numel(), int(flags), _stream(q.device)),
+              "triad_maxmean_fwd_nonneg")
+    return clip, idx, N, sums
+
+
 def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_dT=True, dv_f32=False,
                 flags: int = 0):
     lib = _lib.load()
@@ -220,30 +248,40 @@ class MaxMeanSimilarity(torch.autograd.Function):
     argmax (src/model.py:387-391 and its autograd backward)."""
 
     @staticmethod
-    def forward(ctx, q, v, temperature, scale, flags, uniform_scale=False):
+    def forward(ctx, q, v, temperature, scale, flags, uniform_scale=False, nonneg_lo=None, bwd_pack=False):
+        """nonneg_lo: also produce N = dL/d<q,v> of mean(clamp(S, nonneg_lo, 0)^2) over all token pairs and its sums in
+        the same pass (returned as non-differentiable extras for regularizers.DenseNonNegFromN); else they are None."""
         T = temperature_tensor(temperature, q.device)
-        clip, idx = maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
+        N = sums = None
+        if nonneg_lo is None:
+            clip, idx = maxmean_fwd(q, v, scale, T, want_idx=True, flags=flags)
+        else:
+            numel = float(q.shape[0] * q.shape[1]) * v.shape[0] * v.shape[1]
+            clip, idx, N, sums = maxmean_fwd_nonneg(q, v, scale, T, nonneg_lo, 2.0 / numel, flags=flags)
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(q, v, T, scale, idx, clip)
-        # rows dropped in the forward (zero weight) have no winners recorded: the backward must skip them too
-        ctx.bwd_flags = _lib.BWD_PACK_ROWS if (flags & _lib.FWD_PACK_ROWS) else 0
+        # rows dropped in the forward (zero weight) have no winners recorded: the backward must skip them too (and may
+        # skip zero-weight rows in any case: bwd_pack)
+        ctx.bwd_flags = _lib.BWD_PACK_ROWS if ((flags & _lib.FWD_PACK_ROWS) or bwd_pack) else 0
         if uniform_scale:                       # no attention mask: every row has weight 1/Nq, the dv sort need not look
             ctx.bwd_flags |= _lib.BWD_UNIFORM_SCALE
         ctx.mark_non_differentiable(idx)
+        if N is not None:
+            ctx.mark_non_differentiable(N, sums)
         ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
         ctx.t_dtype = temperature.dtype if isinstance(temperature, torch.Tensor) else None
-        return clip, idx
+        return clip, idx, N, sums
 
     @staticmethod
-    def backward(ctx, g, _gidx):
+    def backward(ctx, g, _gidx, _gN=None, _gsums=None):
         q, v, T, scale, idx, clip = ctx.saved_tensors
         if g is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         need_dq, need_dv, need_dT = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dq, dv, dT = maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq, need_dv, need_dT, flags=ctx.bwd_flags)
         if dT is not None and ctx.t_shape is not None:
             dT = dT.reshape(ctx.t_shape).to(ctx.t_dtype)
-        return dq, dv, dT, None, None, None
+        return dq, dv, dT, None, None, None, None, None
 
 
 class SymmetricInfoNCE(torch.autograd.Function):

@@ -66,6 +66,19 @@ def fused_supported(q: torch.Tensor, v: torch.Tensor) -> bool:
     return q.dtype == torch.bfloat16 and D % 64 == 0 and D <= 512 and (Nv + 7) // 8 * 8 <= 256
 
 
+#: let compute_all_similarities_* produce N in the same pass as the max-mean reduction (triad_maxmean_fwd_nonneg)
+MERGE_FORWARD = True
+
+
+def merged_forward_ok(q: torch.Tensor, v: torch.Tensor) -> bool:
+    """One pass for the max-mean forward and the dense regulariser: the shapes the tcgen05 kernel takes WITHOUT
+    padding (zero patches would take part in the max over patches) and N for all images within the chunk budget."""
+    if not (MERGE_FORWARD and USE_FUSED and fused_supported(q, v)) or v.shape[1] % 8:
+        return False
+    n_bytes = q.shape[0] * q.shape[1] * v.shape[0] * v.shape[1] * 2
+    return n_bytes <= chunk_budget(q.device, CHUNK_BYTES)
+
+
 def nonneg_fused_chunk(q: torch.Tensor, vc: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write_grad: bool,
                        sums: torch.Tensor):
     """N = dl_nonneg/d<q,v> for all rows of q against the images vc ([M, jc*Nv] bf16, or None when write_grad is
@@ -175,7 +188,43 @@ class DenseNonNeg(torch.autograd.Function):
         return gq, gv, gT, None, None
 
 
-def nonneg_pressure(q, v, temperature, lo: float, chunk_bytes=None) -> torch.Tensor:
+class DenseNonNegFromN(torch.autograd.Function):
+    """DenseNonNeg when N = dL/d<q,v> and its sums already came out of the max-mean forward
+    (ops.maxmean_fwd_nonneg): only the two GEMMs dQ = N V, dV = N^T Q are left."""
+
+    @staticmethod
+    def forward(ctx, q, v, temperature, N, sums):
+        Bq, Nq, D = q.shape
+        Bv, Nv, _ = v.shape
+        numel = float(Bq * Nq) * Bv * Nv
+        need = any(ctx.needs_input_grad[:3])
+        if need:
+            q2, v2 = q.contiguous().view(Bq * Nq, D), v.contiguous().view(Bv * Nv, D)
+            dq = torch.mm(N, v2).view(Bq, Nq, D) if ctx.needs_input_grad[0] else None
+            dv = torch.mm(N.t(), q2).view(Bv, Nv, D) if ctx.needs_input_grad[1] else None
+            ctx.save_for_backward(dq, dv, sums[1].to(torch.float32))
+        ctx.need = need
+        ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
+        ctx.t_dtype = temperature.dtype if isinstance(temperature, torch.Tensor) else None
+        return (sums[0] / numel).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gl):
+        if not ctx.need:
+            return None, None, None, None, None
+        dq, dv, dT = ctx.saved_tensors
+        gq = scale_by(dq, gl) if dq is not None else None
+        gv = scale_by(dv, gl) if dv is not None else None
+        gT = None
+        if ctx.needs_input_grad[2] and ctx.t_shape is not None:
+            gT = (dT * gl).reshape(ctx.t_shape).to(ctx.t_dtype)
+        return gq, gv, gT, None, None
+
+
+def nonneg_pressure(q, v, temperature, lo: float, chunk_bytes=None, precomputed=None) -> torch.Tensor:
+    """precomputed: (N, sums) from the merged forward (TokenSims.take_nonneg) for this very (q, v, temperature, lo)."""
+    if precomputed is not None:
+        return DenseNonNegFromN.apply(q, v, temperature, precomputed[0], precomputed[1])
     return DenseNonNeg.apply(q, v, temperature, float(lo), int(CHUNK_BYTES if chunk_bytes is None else chunk_bytes))
 
 
