@@ -459,7 +459,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const float Tval = *p.T;
         const float coefT = p.coef * Tval;
         const float2 cT2 = make_float2(coefT * Tval, coefT * Tval);
-        const double Td = (double)Tval, T2d = (double)Tval * (double)Tval;
+        const float T2f = Tval * Tval;
         const int half = (warp - kEpiWarp0) >> 2;                  // 0: columns [0,128), 1: [128,256)
         const uint32_t stg = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0) * kStgBytesPerWarp;
         const uint32_t stg_row = stg + (uint32_t)lane * 128u;
@@ -505,7 +505,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             // (margin of two bf16 ulps: the reference clamps the bf16-ROUNDED similarity, so a value a hair above
             //  the floor in fp32 can sit on it after rounding)
             if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
-                if (vrow) { s2 += (double)a2s * T2d; sT += (double)a2s * Td; }
+                if (vrow) { s2 += (double)(a2s * T2f); sT += (double)(a2s * Tval); }
             } else {
                 // ---- exact pass (some similarity of this warp's rows is below the clamp floor): redo the tile with
                 //      the clamp and its gradient gate applied, overwriting what the fast pass stored ----
@@ -562,7 +562,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // (see the kMode 1 branch); T is the training-time multiplier there (inv_T == 0)
         const float coefT = p.coef * Tval;
         const float2 cT2 = make_float2(coefT * Tval, coefT * Tval);
-        const double Td = (double)Tval, T2d = (double)Tval * (double)Tval;
+        const float T2f = Tval * Tval;
         const uint32_t stg = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0) * kStgBytesPerWarp;
         const uint32_t stg_row = stg + (uint32_t)lane * 128u;
         const bool wn = kMode == 2 && p.write_n != 0;
@@ -619,31 +619,37 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     uint32_t bufA[32], bufB[32], w[16];
                     tmem_ld32_raw(taddr + own * 32, bufA);
                     tmem_wait_ld();
-#pragma unroll
-                    for (int sq = 0; sq < 8; sq += 2) {
-                        const bool mine = (sq & 2) == 0;                                 // compile-time
-                        const int c = (mine ? own : oth) + (sq >> 2) * 2;                // chunks c, c + 1
-                        tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
-                        mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
-                        if (mine) {
+#pragma unroll 1
+                    for (int b = 0; b < 2; ++b) {                                        // (rolled: half the code, I-cache)
+                        {   // ---- own chunks 2b, 2b + 1: maximum + emission ----
+                            const int c = own + 2 * b;
+                            tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
+                            mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
                             emit_chunk(bufA, c * 32, Nv, cT2, a2, mn, w);
                             if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
-                        }
-                        tmem_wait_ld();
-                        if (sq + 2 < 8) tmem_ld32_raw(taddr + (((sq + 2) & 2) == 0 ? own : oth) * 32 + ((sq + 2) >> 2) * 64, bufA);
-                        mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
-                        if (mine) {
+                            tmem_wait_ld();
+                            tmem_ld32_raw(taddr + (oth + 2 * b) * 32, bufA);
+                            mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
                             emit_chunk(bufB, (c + 1) * 32, Nv, cT2, a2, mn, w);
                             if (wn) { stage_chunk(w, stg_row, lane, 1); if (c * 32 < Nv) emit_box_store(&tmap_n, stg, c * 32, t.j, row0, lane); }
+                            tmem_wait_ld();
                         }
-                        tmem_wait_ld();
+                        {   // ---- the other half's chunks 2b, 2b + 1: maximum only ----
+                            const int c = oth + 2 * b;
+                            tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
+                            mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
+                            tmem_wait_ld();
+                            if (b == 0) tmem_ld32_raw(taddr + (own + 2) * 32, bufA);
+                            mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
+                            tmem_wait_ld();
+                        }
                     }
                 }
                 const bool vrow = r_orig >= 0;
                 const float a2s = (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
                 const float mns = fminf(mn[0], mn[1]) * Tval;
                 if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
-                    if (vrow) { s2 += (double)a2s * T2d; sT += (double)a2s * Td; }
+                    if (vrow) { s2 += (double)(a2s * T2f); sT += (double)(a2s * Tval); }
                 } else {
                     // exact pass for this warp's columns (a similarity at the clamp floor): see the kMode 1 branch
                     float e2 = 0.f, eT = 0.f;
