@@ -38,7 +38,16 @@ def main():
     def both():
         fwd(); bwd()
 
-    for name, fn, n in (("fwd only", fwd, 200), ("bwd only", bwd, 280), ("fwd+bwd", both, 110)):
+    def fwd_1cta():                          # cta_group::1: every CTA loads whole V tiles (2x the L2->SM traffic of the pair)
+        ops.maxmean_fwd(q, v, scale, T, flags=_lib.FWD_FORCE_1CTA)
+
+    def fwd_noidx():                         # forward only (no argmax pass in the epilogue): the epilogue's share of the power
+        ops.maxmean_fwd(q, v, scale, T, want_idx=False)
+
+    runs = (("fwd only", fwd, 200), ("bwd only", bwd, 280), ("fwd+bwd", both, 110))
+    if len(sys.argv) > 1 and sys.argv[1] == "fwd-variants":
+        runs = (("fwd 2cta", fwd, 200), ("fwd 1cta", fwd_1cta, 160), ("fwd 2cta, no argmax pass", fwd_noidx, 200))
+    for name, fn, n in runs:
         torch.cuda.synchronize()
         time.sleep(2.0)
         rows, stop = [], [False]
