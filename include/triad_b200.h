@@ -196,6 +196,15 @@ int triad_maxmean_fwd_nonneg(const void* q, const void* v, const float* row_scal
                              float lo, float coef, void* n_out, long long ldn, double* sums,
                              void* ws, size_t ws_bytes, int flags, void* stream);
 
+/* The two backward GEMMs of the dense regulariser, hand-written (tcgen05, cta_group::2, MN-major operands: no
+ * transposed copies).  n_mat = N = dL/d<q,v> as written by triad_maxmean_fwd_nonneg / triad_nonneg_fused_chunk
+ * ([M][ldn] bf16, Kc = Bv*Nv valid columns).  mode 0: out[M][D] = N . x with x = the patches [Kc][D] (dQ, autograd of
+ * model.py:384-387 w.r.t. the query embeddings); mode 1: out[Kc][D] = N^T . x with x = the tokens [M][D] (dV).
+ * bf16 in, fp32 accumulation, bf16 out; D % 8 == 0, D <= 512.  Deterministic (K splits are added in order). */
+size_t triad_dense_grad_gemm_workspace_bytes(int M, int Kc, int D, int mode);
+int triad_dense_grad_gemm(const void* n_mat, long long ldn, int M, int Kc, const void* x, int D, int mode,
+                          void* out, void* ws, size_t ws_bytes, void* stream);
+
 /* Regularisers on the B POSITIVE pairs only (token_sims[i,i]): temporal smoothness (mode 0, model.py:394-408:
  * mean over (i, a < Nq-1, p) of (S[i,a+1,p] - S[i,a,p])^2) and patch-usage sparsity (mode 1, model.py:528-541:
  * softmax over patches, usage fraction per patch over ALL Nq token rows, mean of relu(frac - threshold)^2).

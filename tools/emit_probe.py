@@ -43,5 +43,27 @@ def main():
     print("copy_ N -> M           ", timed(lambda: M.copy_(N)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "gemms"):
     main()
+
+
+def gemms():
+    """The two backward GEMMs at cfg 2: hand-written (triad_dense_grad_gemm) vs the library."""
+    dev = torch.device("cuda", 0)
+    cfg = bench.CONFIGS[sys.argv[2] if len(sys.argv) > 2 else "cfg2"]
+    (q, v, _), = bench.make_device_inputs(cfg, cfg["B"], 1234, dev, 1)
+    B, Nq, Nv, D = cfg["B"], cfg["Nq"], cfg["Nv"], cfg["D"]
+    N = (torch.randn(B * Nq, B * Nv, device=dev, dtype=torch.bfloat16) * 0.01)
+    q2, v2 = q.view(-1, D), v.view(-1, D)
+    print("dQ = N V     own  ", timed(lambda: ops.dense_grad_gemm(N, v2, 0)))
+    print("dQ = N V     torch", timed(lambda: torch.mm(N, v2)))
+    print("dV = N^T Q   own  ", timed(lambda: ops.dense_grad_gemm(N, q2, 1)))
+    print("dV = N^T Q   torch", timed(lambda: torch.mm(N.t(), q2)))
+    a, b = ops.dense_grad_gemm(N, v2, 0), torch.mm(N, v2)
+    print("rel diff dQ", ((a.float() - b.float()).norm() / b.float().norm()).item())
+    a, b = ops.dense_grad_gemm(N, q2, 1), torch.mm(N.t(), q2)
+    print("rel diff dV", ((a.float() - b.float()).norm() / b.float().norm()).item())
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "gemms":
+    gemms()

@@ -35,8 +35,10 @@ def main():
         total.backward()
         return total
 
-    for reg in (False, True):
+    from triad_b200 import regularizers as R
+    for reg, own in ((False, True), (True, True), (True, False)):
         m.triad_regularizers = reg
+        R.USE_OWN_GEMM = own
         loss = step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,7 +49,7 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         B = cfg["B"]
-        print(f"{cfg['name']}\n  regularisers={reg}: loss {loss.item():.6f}  {ms:.3f} ms/step  {B * B / ms / 1e3:.2f} M pairs/s  "
+        print(f"{cfg['name']}\n  regularisers={reg} own_gemm={own}: loss {loss.item():.6f}  {ms:.3f} ms/step  {B * B / ms / 1e3:.2f} M pairs/s  "
               f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
 
 

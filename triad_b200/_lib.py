@@ -57,6 +57,9 @@ SIGNATURES = {
     "triad_maxmean_fwd_nonneg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p, c_void_p, c_float, c_float, c_void_p, ctypes.c_longlong, c_void_p,
                                          c_void_p, c_size_t, c_int, c_void_p]),
+    "triad_dense_grad_gemm_workspace_bytes": (c_size_t, [c_int] * 4),
+    "triad_dense_grad_gemm": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "triad_pospair_workspace_bytes": (c_size_t, [c_int]),
     "triad_pospair_terms": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),

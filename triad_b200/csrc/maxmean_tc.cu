@@ -783,6 +783,22 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const cuuint6
     return TRIAD_OK;
 }
 
+// fp32, rank 3, SWIZZLE_128B (32-column boxes: the fp32 partial tiles of dense_gemm.cu)
+int encode_tmap_f32_3d(CUtensorMap* map, const void* base, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+    tc::PFN_tmapEncodeTiled fn = tc::get_encode_fn();
+    if (!fn) return fail_msg(TRIAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (fp32) failed (CUresult %d)", (int)r);
+        return fail_msg(TRIAD_ERR_CUDA, buf);
+    }
+    return TRIAD_OK;
+}
+
 namespace tc {
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,

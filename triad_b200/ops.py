@@ -170,6 +170,29 @@ def maxmean_fwd_nonneg(q: torch.Tensor, v: torch.Tensor, scale: torch.Tensor, T:
     return clip, idx, N, sums
 
 
+def dense_grad_gemm(N: torch.Tensor, x: torch.Tensor, mode: int) -> torch.Tensor:
+    """mode 0: N @ x (N [M,Kc] bf16, x [Kc,D]); mode 1: N.t() @ x (x [M,D]) — the dense regulariser's two backward GEMMs
+    on the tensor cores (triad_dense_grad_gemm: MN-major operands, no transposed copies).  bf16 out."""
+    lib = _lib.load()
+    _require_cuda(N, x)
+    if N.dtype != torch.bfloat16 or x.dtype != torch.bfloat16 or N.dim() != 2 or x.dim() != 2:
+        raise TypeError("dense_grad_gemm takes 2-D bfloat16 matrices")
+    if N.stride(1) != 1:
+        raise ValueError("N must be row-major")
+    x = x.contiguous()
+    M, Kc = N.shape
+    D = x.shape[1]
+    if x.shape[0] != (Kc if mode == 0 else M):
+        raise ValueError("dense_grad_gemm: inner dimensions differ")
+    out = torch.empty(M if mode == 0 else Kc, D, dtype=torch.bfloat16, device=N.device)
+    nws = lib.triad_dense_grad_gemm_workspace_bytes(M, Kc, D, int(mode))
+    with _on(N):
+        ws = _Workspace.get(nws, N.device, "dgemm")
+        check(lib.triad_dense_grad_gemm(N.data_ptr(), N.stride(0), M, Kc, x.data_ptr(), D, int(mode), out.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream(N.device)), "triad_dense_grad_gemm")
+    return out
+
+
 def maxmean_bwd(q, v, idx, g, clip, scale, T, need_dq=True, need_dv=True, need_dT=True, dv_f32=False,
                 flags: int = 0):
     lib = _lib.load()

@@ -66,6 +66,20 @@ def fused_supported(q: torch.Tensor, v: torch.Tensor) -> bool:
     return q.dtype == torch.bfloat16 and D % 64 == 0 and D <= 512 and (Nv + 7) // 8 * 8 <= 256
 
 
+#: the two backward GEMMs dQ = N V, dV = N^T Q on the hand-written tcgen05 kernel (triad_dense_grad_gemm, MN-major
+#: operands); False: the library's GEMM (kept as a cross-check and for fp32)
+USE_OWN_GEMM = True
+
+
+def grad_gemms(N: torch.Tensor, q2: torch.Tensor, v2: torch.Tensor, need_dq: bool = True, need_dv: bool = True):
+    """dQ [M,D] = N v2, dV [Kc,D] = N^T q2 for N = dL/d<q,v> [M,Kc]."""
+    own = USE_OWN_GEMM and N.dtype == torch.bfloat16 and q2.dtype == torch.bfloat16 and q2.shape[1] % 8 == 0 and q2.shape[1] <= 512 \
+        and N.stride(1) == 1 and N.stride(0) % 8 == 0
+    if own:
+        return (ops.dense_grad_gemm(N, v2, 0) if need_dq else None, ops.dense_grad_gemm(N, q2, 1) if need_dv else None)
+    return (torch.mm(N, v2) if need_dq else None, torch.mm(N.t(), q2) if need_dv else None)
+
+
 #: let compute_all_similarities_* produce N in the same pass as the max-mean reduction (triad_maxmean_fwd_nonneg)
 MERGE_FORWARD = True
 
@@ -125,11 +139,12 @@ def nonneg_sweep(q: torch.Tensor, v: torch.Tensor, T: torch.Tensor, lo: float, n
             S = torch.mm(q2, vc.t())                        # raw <q,v>, rounded to the input dtype like the reference's matmul
             nonneg_chunk(S, T, lo, 2.0 / numel, need_grads, sums)  # in place: S -> N = dl_nonneg/d<q,v>
         if need_grads:
+            dq_c, dv_c = grad_gemms(S, q2, vc)
             if single:
-                dq = torch.mm(S, vc)
+                dq = dq_c
             else:
-                dq.add_(torch.mm(S, vc))
-            torch.mm(S.t(), q2, out=dv[j0:j0 + jc].view(-1, D))
+                dq.add_(dq_c)
+            dv[j0:j0 + jc] = dv_c.view(-1, Nv, D)
     if dv is not None and Nv != Nv_true:
         dv = dv[:, :Nv_true].contiguous()
     return sums, dq, dv
@@ -200,8 +215,9 @@ class DenseNonNegFromN(torch.autograd.Function):
         need = any(ctx.needs_input_grad[:3])
         if need:
             q2, v2 = q.contiguous().view(Bq * Nq, D), v.contiguous().view(Bv * Nv, D)
-            dq = torch.mm(N, v2).view(Bq, Nq, D) if ctx.needs_input_grad[0] else None
-            dv = torch.mm(N.t(), q2).view(Bv, Nv, D) if ctx.needs_input_grad[1] else None
+            dq, dv = grad_gemms(N, q2, v2, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+            dq = dq.view(Bq, Nq, D) if dq is not None else None
+            dv = dv.view(Bv, Nv, D) if dv is not None else None
             ctx.save_for_backward(dq, dv, sums[1].to(torch.float32))
         ctx.need = need
         ctx.t_shape = temperature.shape if isinstance(temperature, torch.Tensor) else None
