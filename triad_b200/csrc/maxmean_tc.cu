@@ -540,6 +540,98 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
             p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
         }
+    } else if (kMode == 2 && warp >= kEpiWarp0 + 4) {
+        // ============ kMode 2, emission warps (one per TMEM lane quarter, all 256 columns) =============
+        // Same arithmetic as the kMode 1 branch.  The max-mean epilogue runs beside it in warps 4-7 (one warp per
+        // quarter, the round-1 arrangement): two independent ~1 000-instruction chains per scheduler instead of two
+        // ~1 500-instruction ones doing both jobs.  The 8 KB of staging per warp are two boxes: box b leaves
+        // through the TMA unit while box b+1 is filled (cp.async.bulk.wait_group.read 1).
+        const int quarter = warp & 3;
+        const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
+        const float Tval = *p.T;
+        const float coefT = p.coef * Tval;
+        const float2 cT2 = make_float2(coefT * Tval, coefT * Tval);
+        const float T2f = Tval * Tval;
+        const uint32_t stg0 = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0 - 4) * 2u * kStgBytesPerWarp;
+        const bool wn = p.write_n != 0;
+        double s2 = 0.0, sT = 0.0;
+        uint32_t t_cnt = 0, nbox = 0;                               // nbox: bulk groups committed so far (staging box = nbox & 1)
+        bool alive = true;
+        Tile t;
+        while (alive && it.next(t)) {
+            const int wrow0 = t.m * kTileRows + (int)cta_rank * kBlockM + quarter * 32;      // the warp's first row
+            const bool vrow = wrow0 + lane < p.M;
+            const uint32_t acc = t_cnt & 1u, acc_phase = (t_cnt >> 1) & 1u;
+            ++t_cnt;
+            bool ok = mbar_wait(bar_t_full + 8 * acc, acc_phase, p.abort_flag, 6);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) { alive = false; break; }
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxN;
+            float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+            float mn[2] = {0.f, 0.f};
+            {
+                uint32_t bufA[32], bufB[32], w[16];
+                tmem_ld32_raw(taddr, bufA);
+                tmem_wait_ld();
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {                                             // (rolled: I-cache)
+                    const int c = 2 * b;
+                    const uint32_t stg = stg0 + (nbox & 1u) * kStgBytesPerWarp;
+                    const uint32_t stg_row = stg + (uint32_t)lane * 128u;
+                    tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
+                    emit_chunk(bufA, c * 32, p.Nv, cT2, a2, mn, w);
+                    if (wn) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the box before last has been read
+                        __syncwarp();
+                        stage_chunk(w, stg_row, lane, 0);
+                    }
+                    tmem_wait_ld();
+                    tmem_ld32_raw(taddr + ((c + 2) & 7) * 32, bufA);                     // (b == 3: a harmless re-load of chunk 0)
+                    emit_chunk(bufB, (c + 1) * 32, p.Nv, cT2, a2, mn, w);
+                    if (wn) { stage_chunk(w, stg_row, lane, 1); if (c * 32 < p.Nv) { emit_box_store(&tmap_n, stg, c * 32, t.j, wrow0, lane); ++nbox; } }
+                    tmem_wait_ld();
+                }
+            }
+            const float a2s = (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
+            const float mns = fminf(mn[0], mn[1]) * Tval;
+            if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
+                if (vrow) { s2 += (double)(a2s * T2f); sT += (double)(a2s * Tval); }
+            } else {
+                // exact pass (a similarity of this warp's rows is at the clamp floor): see the kMode 1 branch
+                float e2 = 0.f, eT = 0.f;
+                if (wn) emit_box_drain(lane);
+                for (int b = 0; b < 4; ++b) {
+                    const int c = 2 * b;
+                    if (c * 32 >= p.Nv) break;                                           // warp-uniform
+                    const uint32_t stg = stg0 + (nbox & 1u) * kStgBytesPerWarp;
+                    const uint32_t stg_row = stg + (uint32_t)lane * 128u;
+                    uint32_t buf[32], w[16];
+                    tmem_ld32_raw(taddr + c * 32, buf);
+                    tmem_wait_ld();
+                    emit_chunk_exact(buf, c * 32, p.Nv, Tval, coefT, p.lo, e2, eT, w);
+                    if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
+                    tmem_ld32_raw(taddr + (c + 1) * 32, buf);
+                    tmem_wait_ld();
+                    emit_chunk_exact(buf, (c + 1) * 32, p.Nv, Tval, coefT, p.lo, e2, eT, w);
+                    if (wn) { stage_chunk(w, stg_row, lane, 1); emit_box_store(&tmap_n, stg, c * 32, t.j, wrow0, lane); ++nbox; }
+                }
+                if (vrow) { s2 += (double)e2; sT += (double)eT; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtaGroup == 2) mbar_arrive_cluster(t_empty_sig + 8 * acc);
+                else mbar_arrive_local(bar_t_empty + 8 * acc);
+            }
+        }
+        emit_box_reusable(lane);                                    // the staging boxes must outlive the last bulk reads
+        s2 = warp_sum_d(s2);
+        sT = warp_sum_d(sT);
+        if (lane == 0) {
+            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
+            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
+        }
     } else if (warp >= kEpiWarp0 && (p.idx != nullptr || warp < kEpiWarp0 + 4)) {
         // =============================== epilogue =======================================
         // Two warps per TMEM lane quarter (one per scheduler pair): both take the row maximum over all columns
@@ -548,6 +640,9 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // of shared memory and a 64-thread named barrier, and the lower-half warp alone writes idx / partial sums.
         // (One warp per scheduler has to issue ~1 600 dependent instructions per tile within the tile's MMA time.)
         // Forward-only calls (no idx) have no second pass: the upper-half warps sit out.
+        // kMode 2: ONE warp per lane quarter does the whole max-mean epilogue (all columns in both passes, no exchange);
+        // the other four epilogue warps are the emission warps above.
+        constexpr bool kSolo = kMode == 2;
         const int quarter = warp & 3;
         const int half = (warp - kEpiWarp0) >> 2;
         const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
@@ -558,15 +653,6 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         int r_orig = -1, qi = 0, piece = 0;       // original row (-1: no such row), its query, packed partial slot
         const size_t idx_pitch = (size_t)(p.M / p.Nq) * p.nq_pad;
         float R_run = 0.f; int best_run = 0;      // running (rounded max, first argmax) across the sub-tiles of an image
-        // kMode 2: this warp also emits N = dL/d<q,v> of the non-negative pressure term for ITS half of the columns
-        // (see the kMode 1 branch); T is the training-time multiplier there (inv_T == 0)
-        const float coefT = p.coef * Tval;
-        const float2 cT2 = make_float2(coefT * Tval, coefT * Tval);
-        const float T2f = Tval * Tval;
-        const uint32_t stg = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0) * kStgBytesPerWarp;
-        const uint32_t stg_row = stg + (uint32_t)lane * 128u;
-        const bool wn = kMode == 2 && p.write_n != 0;
-        double s2 = 0.0, sT = 0.0;
         bool alive = true;
         Tile t;
         while (alive && it.next(t)) {
@@ -595,7 +681,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             //      are masked by Nv — which keeps every load unconditional (see tmem_ld32_raw). ----
             constexpr int kCh = kMaxN / 32;
             float mx = -INFINITY;
-            if constexpr (kMode != 2) {
+            {
                 uint32_t bufA[32], bufB[32];
                 tmem_ld32_raw(taddr, bufA);
                 tmem_wait_ld();
@@ -608,67 +694,6 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
                     tmem_wait_ld();
                 }
-            } else {
-                // ---- pass 1 + dense-regulariser emission.  Chunk order: own 0,1 | other 0,1 | own 2,3 | other 2,3
-                //      (own = this warp's half of the columns): each staged 64-column box leaves through the TMA unit
-                //      while the other half's chunks are reduced, so the staging box is free again when needed. ----
-                const int own = half * 4, oth = 4 - own;
-                float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-                float mn[2] = {0.f, 0.f};
-                {
-                    uint32_t bufA[32], bufB[32], w[16];
-                    tmem_ld32_raw(taddr + own * 32, bufA);
-                    tmem_wait_ld();
-#pragma unroll 1
-                    for (int b = 0; b < 2; ++b) {                                        // (rolled: half the code, I-cache)
-                        {   // ---- own chunks 2b, 2b + 1: maximum + emission ----
-                            const int c = own + 2 * b;
-                            tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
-                            mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
-                            emit_chunk(bufA, c * 32, Nv, cT2, a2, mn, w);
-                            if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
-                            tmem_wait_ld();
-                            tmem_ld32_raw(taddr + (oth + 2 * b) * 32, bufA);
-                            mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
-                            emit_chunk(bufB, (c + 1) * 32, Nv, cT2, a2, mn, w);
-                            if (wn) { stage_chunk(w, stg_row, lane, 1); if (c * 32 < Nv) emit_box_store(&tmap_n, stg, c * 32, t.j, row0, lane); }
-                            tmem_wait_ld();
-                        }
-                        {   // ---- the other half's chunks 2b, 2b + 1: maximum only ----
-                            const int c = oth + 2 * b;
-                            tmem_ld32_raw(taddr + (c + 1) * 32, bufB);
-                            mx = fmaxf(mx, chunk_max32(bufA, c * 32, Nv));
-                            tmem_wait_ld();
-                            if (b == 0) tmem_ld32_raw(taddr + (own + 2) * 32, bufA);
-                            mx = fmaxf(mx, chunk_max32(bufB, (c + 1) * 32, Nv));
-                            tmem_wait_ld();
-                        }
-                    }
-                }
-                const bool vrow = r_orig >= 0;
-                const float a2s = (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
-                const float mns = fminf(mn[0], mn[1]) * Tval;
-                if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
-                    if (vrow) { s2 += (double)(a2s * T2f); sT += (double)(a2s * Tval); }
-                } else {
-                    // exact pass for this warp's columns (a similarity at the clamp floor): see the kMode 1 branch
-                    float e2 = 0.f, eT = 0.f;
-                    if (wn) emit_box_drain(lane);
-                    for (int b = 0; b < 2; ++b) {
-                        const int c = own + 2 * b;
-                        if (c * 32 >= Nv) break;                                         // warp-uniform
-                        uint32_t buf[32], w[16];
-                        tmem_ld32_raw(taddr + c * 32, buf);
-                        tmem_wait_ld();
-                        emit_chunk_exact(buf, c * 32, Nv, Tval, coefT, p.lo, e2, eT, w);
-                        if (wn) { emit_box_reusable(lane); stage_chunk(w, stg_row, lane, 0); }
-                        tmem_ld32_raw(taddr + (c + 1) * 32, buf);
-                        tmem_wait_ld();
-                        emit_chunk_exact(buf, (c + 1) * 32, Nv, Tval, coefT, p.lo, e2, eT, w);
-                        if (wn) { stage_chunk(w, stg_row, lane, 1); emit_box_store(&tmap_n, stg, c * 32, t.j, row0, lane); }
-                    }
-                    if (vrow) { s2 += (double)e2; sT += (double)eT; }
-                }
             }
             float R;
             const float theta = argmax_threshold<true>(mx, Tval, &R);
@@ -679,8 +704,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             //      compare/select chains instead of one 256-long dependent chain. ----
             int best = (int)kNoCol;
             if (p.idx != nullptr) {
-                constexpr int kHalfCh = kCh / 2;
-                const int cb = half * kHalfCh;                   // this warp's chunks: [cb, cb + kHalfCh)
+                constexpr int kHalfCh = kSolo ? kCh : kCh / 2;
+                const int cb = kSolo ? 0 : half * kHalfCh;       // this warp's chunks: [cb, cb + kHalfCh)
                 uint32_t bufA[32], bufB[32];
                 tmem_ld32_raw(taddr + (cb + kHalfCh - 1) * 32, bufA);
                 tmem_wait_ld();
@@ -702,7 +727,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 if constexpr (kCtaGroup == 2) mbar_arrive_cluster(t_empty_sig + 8 * acc);
                 else mbar_arrive_local(bar_t_empty + 8 * acc);
             }
-            if (p.idx != nullptr) {
+            if (p.idx != nullptr && !kSolo) {
                 // pair exchange (double buffered by tile parity: the upper-half warp may already be one tile ahead)
                 const uint32_t slot = xch_smem + ((t_cnt & 1u) * 128u + (uint32_t)(quarter * 32 + lane)) * 2u;
                 if (half == 1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(slot), "h"((uint16_t)best) : "memory");
@@ -713,6 +738,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     if (best == (int)kNoCol) best = (other == kNoCol) ? 0 : (int)other;
                 }
             }
+            if (kSolo && best == (int)kNoCol) best = 0;
             if (half == 1) continue;                             // the lower-half warp owns the outputs
             // Equal rounded maxima in two sub-tiles: the earlier one holds the first index (torch.max), and
             // inside a sub-tile `best` already is the first column of that rounded value.
@@ -727,15 +753,6 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const float val = (r_orig >= 0) ? R_run * rs : 0.f;
             if (p.pack_off == nullptr) store_group_partials(p.part, t.j, row0 >> 5, p.G, p.S, row0, p.M, p.Nq, val, lane);
             else store_group_partials_packed(p.part, t.j, p.Bq, p.pieces, qi, piece, val, lane);
-        }
-        if constexpr (kMode == 2) {
-            emit_box_reusable(lane);                                // the staging box must outlive the last bulk read
-            s2 = warp_sum_d(s2);
-            sT = warp_sum_d(sT);
-            if (lane == 0) {
-                p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
-                p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
-            }
         }
     }
 
