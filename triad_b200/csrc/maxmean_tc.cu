@@ -138,6 +138,13 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// compensated (Kahan) fp32 accumulation: s + c-correction carries ~fp64 accuracy over a few thousand terms
+__device__ __forceinline__ void kahan_add(float& s, float& c, float x) {
+    const float y = x - c;
+    const float t = s + y;
+    c = (t - s) - y;
+    s = t;
+}
 __device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(reinterpret_cast<unsigned long long&>(acc))
         : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
@@ -298,8 +305,11 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   const __grid_constant__ CUtensorMap tmap_n, const Params p) {
     constexpr bool kEmitN = kMode != 0;
     constexpr int kVStageBytes = (kMaxN / kCtaGroup) * kBlockK * 2;       // 32 KB / 16 KB
-    // the dense-regulariser modes give the last 32 KB of the ring to the epilogue's store staging (8 warps x 4 KB)
-    constexpr int kStages = (kVRingBytes - (kEmitN ? kStgBytes : 0)) / kVStageBytes;   // 3 / 6  (2 / 4)
+    // the dense-regulariser modes give the last 32 KB of the ring to the epilogue's store staging: kMode 1 eight warps x
+    // one 4 KB box (32 rows x 64 columns), kMode 2 four emission warps x two such boxes.  (Two 2 KB boxes of 32 columns
+    // per emission warp, i.e. 5 ring stages instead of 4, were measured: no faster, twice the bulk stores.)
+    constexpr uint32_t kStgTotal = kMode != 0 ? kStgBytes : 0u;
+    constexpr int kStages = (kVRingBytes - kStgTotal) / kVStageBytes;                  // 3 / 6  (2 / 4)
     constexpr int kTileRows = kBlockM * kCtaGroup;
 
     extern __shared__ uint8_t smem_raw[];
@@ -544,8 +554,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // ============ kMode 2, emission warps (one per TMEM lane quarter, all 256 columns) =============
         // Same arithmetic as the kMode 1 branch.  The max-mean epilogue runs beside it in warps 4-7 (one warp per
         // quarter, the round-1 arrangement): two independent ~1 000-instruction chains per scheduler instead of two
-        // ~1 500-instruction ones doing both jobs.  The 8 KB of staging per warp are two boxes: box b leaves
-        // through the TMA unit while box b+1 is filled (cp.async.bulk.wait_group.read 1).
+        // ~1 500-instruction ones doing both jobs.  The 8 KB of staging per warp are two 32 x 64 boxes: a box leaves
+        // through the TMA unit while the next one is filled (cp.async.bulk.wait_group.read 1).
         const int quarter = warp & 3;
         const uint32_t t_empty_sig = (kCtaGroup == 2) ? mapa(bar_t_empty, 0) : bar_t_empty;
         const float Tval = *p.T;
@@ -554,7 +564,8 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const float T2f = Tval * Tval;
         const uint32_t stg0 = v_smem + (uint32_t)kStages * (uint32_t)kVStageBytes + (uint32_t)(warp - kEpiWarp0 - 4) * 2u * kStgBytesPerWarp;
         const bool wn = p.write_n != 0;
-        double s2 = 0.0, sT = 0.0;
+        // per-tile sums are added with a compensated fp32 sum (an fp64 add per tile and lane is 1/64-rate on this chip)
+        float s2 = 0.f, s2c = 0.f, sT = 0.f, sTc = 0.f;
         uint32_t t_cnt = 0, nbox = 0;                               // nbox: bulk groups committed so far (staging box = nbox & 1)
         bool alive = true;
         Tile t;
@@ -596,7 +607,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             const float a2s = (a2[0].x + a2[0].y) + (a2[1].x + a2[1].y);
             const float mns = fminf(mn[0], mn[1]) * Tval;
             if (!__any_sync(0xffffffffu, vrow && mns < p.lo * (1.0f - 1.0f / 64.0f))) {
-                if (vrow) { s2 += (double)(a2s * T2f); sT += (double)(a2s * Tval); }
+                if (vrow) { kahan_add(s2, s2c, a2s * T2f); kahan_add(sT, sTc, a2s * Tval); }
             } else {
                 // exact pass (a similarity of this warp's rows is at the clamp floor): see the kMode 1 branch
                 float e2 = 0.f, eT = 0.f;
@@ -616,7 +627,7 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     emit_chunk_exact(buf, (c + 1) * 32, p.Nv, Tval, coefT, p.lo, e2, eT, w);
                     if (wn) { stage_chunk(w, stg_row, lane, 1); emit_box_store(&tmap_n, stg, c * 32, t.j, wrow0, lane); ++nbox; }
                 }
-                if (vrow) { s2 += (double)e2; sT += (double)eT; }
+                if (vrow) { kahan_add(s2, s2c, e2); kahan_add(sT, sTc, eT); }
             }
             tc_fence_before();
             __syncwarp();
@@ -626,11 +637,11 @@ maxmean_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         }
         emit_box_reusable(lane);                                    // the staging boxes must outlive the last bulk reads
-        s2 = warp_sum_d(s2);
-        sT = warp_sum_d(sT);
+        const double s2d = warp_sum_d((double)s2 - (double)s2c);
+        const double sTd = warp_sum_d((double)sT - (double)sTc);
         if (lane == 0) {
-            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2;
-            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sT * (double)p.coef;
+            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2] = s2d;
+            p.n_partials[(size_t)(blockIdx.x * kEmitEpiWarps + (warp - kEpiWarp0)) * 2 + 1] = sTd * (double)p.coef;
         }
     } else if (warp >= kEpiWarp0 && (p.idx != nullptr || warp < kEpiWarp0 + 4)) {
         // =============================== epilogue =======================================
@@ -783,15 +794,16 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 
 }  // namespace tc
 
-// bf16 tiled tensor map, rank 2 or 3; swizzle128 selects SWIZZLE_128B (UMMA operands) or none (plain row tiles)
+// bf16 tiled tensor map, rank 2 or 3; swizzle: 0 none (plain row tiles), 1 SWIZZLE_128B (UMMA operands, 64-column store
+// boxes), 2 SWIZZLE_64B (32-column store boxes)
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                     const cuuint32_t* box, bool swizzle128) {
+                     const cuuint32_t* box, int swizzle) {
     tc::PFN_tmapEncodeTiled fn = tc::get_encode_fn();
     if (!fn) return fail_msg(TRIAD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[96];
         snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -934,7 +946,7 @@ int launch_maxmean_tc(const void* q, const void* v, const float* row_scale, cons
         cuuint64_t dims[3] = {(cuuint64_t)Nv, (cuuint64_t)Bv, (cuuint64_t)M};
         cuuint64_t strides[2] = {(cuuint64_t)Nv * 2, (cuuint64_t)emit->ldn * 2};
         cuuint32_t box[3] = {64, 1, 32};
-        int rc = encode_map(&mn, emit->n_out, 3, dims, strides, box);
+        int rc = encode_tmap_bf16(&mn, emit->n_out, 3, dims, strides, box, 1);
         if (rc) return rc;
     }
     const long long total = (long long)n_m * Bv;
