@@ -128,3 +128,29 @@ def test_full_loss_uses_the_merged_forward_and_matches_the_separate_passes():
         assert ((a[1] - b[1]).norm() / b[1].norm()).item() < 4e-3               # bf16 roundings of the summands differ
         assert ((a[2] - b[2]).norm() / b[2].norm()).item() < 4e-3
         assert abs(a[3] - b[3]) <= 1e-4 * abs(b[3]) + 1e-7
+
+
+def test_handle_reuse_and_retained_graph():
+    """The handle hands N over once: a second loss call on the same handle falls back to the separate regulariser pass
+    and gives the same value; backward twice through a retained graph accumulates exactly twice the gradient."""
+    import triad_b200
+    q, v = _inputs(8, 8, 50, 256, 512, 21)
+    m = triad_b200.TriadHotPath(1.5).cuda()
+    qd, vd = q.clone().requires_grad_(), v.clone().requires_grad_()
+    clip, tok = m.compute_all_similarities_av(qd, vd)
+    assert tok.nonneg is not None
+    t1 = m.compute_contrastive_loss_av(clip, tok)[0]
+    assert tok.nonneg is None
+    t2 = m.compute_contrastive_loss_av(clip, tok)[0]
+    assert abs(t1.item() - t2.item()) <= 1e-6 * abs(t1.item())
+    t1.backward(retain_graph=True)
+    g1 = qd.grad.float().clone()
+    t1.backward()
+    g2 = qd.grad.float()
+    assert ((g2 - 2 * g1).norm() / g1.norm()).item() < 8e-3          # bf16 accumulation of two equal gradients
+    # evaluation without gradients never takes the merged path (nothing to hand over)
+    with torch.no_grad():
+        clip3, tok3 = m.compute_all_similarities_av(q, v)
+        assert tok3.nonneg is None
+        t3 = m.compute_contrastive_loss_av(clip3, tok3)[0]
+    assert abs(t3.item() - t1.item()) <= 1e-5 * abs(t1.item())

@@ -42,7 +42,7 @@ constexpr uint32_t kABytes = 2 * kBoxBytes;                     // 16 KB: 128 ro
 constexpr uint32_t kBHalfBytes = 2 * kBoxBytes;                 // 16 KB: this CTA's 128 of a half's 256 columns x 64 k
 constexpr uint32_t kStageBytes = kABytes + 2 * kBHalfBytes;     // 48 KB
 constexpr uint32_t kStgPerWarp = 32 * 128;                      // 32 rows x 32 fp32
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 4 * kStgPerWarp + 1024 + 1024;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 4 * 2 * kStgPerWarp + 1024 + 1024;   // 226 KB
 
 struct Params {
     int n_tiles;          // 256-row tiles of the output
@@ -65,14 +65,14 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
     return d;
 }
 
-template <bool kAMN>
+template <bool kAMN, int kHalves>
 __global__ void __launch_bounds__(kThreads, 1)
 dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ CUtensorMap tmap_c, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stg0 = base + kStages * kStageBytes;
-    const uint32_t bar = stg0 + 4 * kStgPerWarp;
+    const uint32_t bar = stg0 + 4 * 2 * kStgPerWarp;
     const uint32_t bar_full = bar, bar_empty = bar + 8 * kStages;
     const uint32_t bar_t_full = bar_empty + 8 * kStages, bar_t_empty = bar_t_full + 8;
     const uint32_t tmem_slot = bar_t_empty + 8;
@@ -84,7 +84,7 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     const bool is_leader = cta_rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int n_items = p.n_tiles * p.splits;
-    const uint32_t b_bytes = (uint32_t)p.n_halves * kBHalfBytes;
+    constexpr uint32_t b_bytes = (uint32_t)kHalves * kBHalfBytes;
 
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_c); }
     if (warp == 1 && lane == 0) {
@@ -120,7 +120,8 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         tma_load_2d<2>(st, &tmap_a, full_sig + 8 * s, m0, kb * kBlockK);                     // boxes {64 m, 64 k}
                         tma_load_2d<2>(st + kBoxBytes, &tmap_a, full_sig + 8 * s, m0 + 64, kb * kBlockK);
                     }
-                    for (int h = 0; h < p.n_halves; ++h) {
+#pragma unroll
+                    for (int h = 0; h < kHalves; ++h) {
                         const int n0 = h * kHalfN + (int)cta_rank * (kHalfN / 2);
                         const uint32_t bs = st + kABytes + h * kBHalfBytes;
                         tma_load_2d<2>(bs, &tmap_b, full_sig + 8 * s, n0, kb * kBlockK);
@@ -137,6 +138,10 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             const bool issuer = elect_one();
             const uint32_t idesc = make_idesc(kTileM, kHalfN) | (kAMN ? (1u << 15) : 0u) | (1u << 16);
             const uint32_t tm = __shfl_sync(0xffffffffu, tmem0, 0);
+            // descriptors of stage 0; a stage / a K = 16 step / an N half are added to the start-address field (>> 4), so
+            // everything stays in uniform registers and the eight MMAs of a k-block issue back to back
+            const uint64_t a_desc0 = kAMN ? make_desc_mn(base) : make_smem_desc(base);
+            const uint64_t b_desc0 = make_desc_mn(base + kABytes);
             int s = 0; uint32_t ph = 0, tph = 0; bool ok = true;
             for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
                 const int tile = it / p.splits, sp = it - tile * p.splits;
@@ -148,16 +153,15 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                     ok = mbar_wait(bar_full + 8 * s, ph, p.abort_flag, 33);
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t st = base + s * kStageBytes;
-                    const uint64_t a_desc = kAMN ? make_desc_mn(st) : make_smem_desc(st);
-                    const uint64_t b_desc = make_desc_mn(st + kABytes);
+                    const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)s * (kStageBytes >> 4));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)s * (kStageBytes >> 4));
                     if (issuer) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            const uint64_t ad = a_desc + (uint64_t)(kAMN ? 128u * k : 2u * k);   // 2 KB / 32 B per K = 16 step (>> 4)
-                            for (int h = 0; h < p.n_halves; ++h)
-                                umma_bf16<2>(tm + h * kHalfN, ad, b_desc + (uint64_t)(h * (kBHalfBytes >> 4) + 128u * k), idesc,
-                                             (uint32_t)((kb != kb0) | (k != 0)));
+#pragma unroll
+                            for (int h = 0; h < kHalves; ++h)
+                                umma_bf16<2>(tm + h * kHalfN, a_desc + (uint64_t)(kAMN ? 128u * k : 2u * k),       // 2 KB / 32 B per K = 16 step
+                                             b_desc + (uint64_t)(h * (kBHalfBytes >> 4) + 128u * k), idesc, (uint32_t)((kb != kb0) | (k != 0)));
                         }
                         umma_commit<2>(bar_empty + 8 * s);
                     }
@@ -174,10 +178,9 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         // =============================== epilogue (both CTAs): fp32 partial tile out ======
         const int quarter = warp & 3;
         const uint32_t t_empty_sig = mapa(bar_t_empty, 0);
-        const uint32_t stg = stg0 + (uint32_t)quarter * kStgPerWarp;
-        const uint32_t stg_row = stg + (uint32_t)lane * 128u;
+        const uint32_t stg_w = stg0 + (uint32_t)quarter * 2u * kStgPerWarp;      // two boxes: one leaves while the other fills
         const uint32_t taddr = tmem0 + ((uint32_t)(quarter * 32) << 16);
-        uint32_t tph = 0; bool ok = true;
+        uint32_t tph = 0, nbox = 0; bool ok = true;
         for (int it = cluster_id; it < n_items && ok; it += n_clusters) {
             const int tile = it / p.splits, sp = it - tile * p.splits;
             const int row0 = tile * kTileM + (int)cta_rank * kCtaM + quarter * 32;
@@ -185,11 +188,13 @@ dgemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             tc_fence_after();
-            for (int c = 0; c * 32 < p.D; ++c) {
+            for (int c = 0; c * 32 < p.D; ++c, ++nbox) {
+                const uint32_t stg = stg_w + (nbox & 1u) * kStgPerWarp;
+                const uint32_t stg_row = stg + (uint32_t)lane * 128u;
                 uint32_t buf[32];
                 tmem_ld32_raw(taddr + c * 32, buf);
                 tmem_wait_ld();
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the box has been read
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the box before last has been read
                 __syncwarp();
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
@@ -340,15 +345,15 @@ extern "C" int triad_dense_grad_gemm(const void* n_mat, long long ldn, int M, in
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (mode == 0) {
-        auto kern = dgemm_kernel<false>;
-        TRIAD_SET_MAX_SMEM(kern, kSmemBytes);
-        TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
-    } else {
-        auto kern = dgemm_kernel<true>;
-        TRIAD_SET_MAX_SMEM(kern, kSmemBytes);
-        TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));
-    }
+#define TRIAD_DGEMM_LAUNCH(AMN, HALVES)                                                         \
+    do {                                                                                       \
+        auto kern = dgemm_kernel<AMN, HALVES>;                                                 \
+        TRIAD_SET_MAX_SMEM(kern, kSmemBytes);                                                  \
+        TRIAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p));                       \
+    } while (0)
+    if (mode == 0) { if (p.n_halves == 2) TRIAD_DGEMM_LAUNCH(false, 2); else TRIAD_DGEMM_LAUNCH(false, 1); }
+    else           { if (p.n_halves == 2) TRIAD_DGEMM_LAUNCH(true, 2);  else TRIAD_DGEMM_LAUNCH(true, 1); }
+#undef TRIAD_DGEMM_LAUNCH
     count_launch();
     const size_t n4 = (size_t)rows_out * D / 4;
     size_t want = (n4 + 255) / 256;

@@ -63,6 +63,7 @@ smooth_kernel(const void* __restrict__ raw, const float* __restrict__ Tptr, int 
     const int a_step = (int)(gridDim.x % (unsigned)Nq);
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
         const size_t k0 = (size_t)r * Nv;
+        float r2 = 0.f, rT = 0.f;                                       // this row's share in fp32 (an fp64 add is 1/64 rate)
         for (int p = threadIdx.x; p < Nv; p += kThreads) {
             const size_t k = k0 + p;
             const float r0 = Elt<T>::load(raw, k);
@@ -71,10 +72,11 @@ smooth_kernel(const void* __restrict__ raw, const float* __restrict__ Tptr, int 
             if (a > 0) dprev = s0 - Elt<T>::scaled(Elt<T>::load(raw, k - Nv), Tv);
             if (a + 1 < Nq) dnext = Elt<T>::scaled(Elt<T>::load(raw, k + Nv), Tv) - s0;
             const float gs = c * (dprev - dnext);                       // d value / dS[i,a,p]
-            s2 += (double)(dnext * dnext);                              // every difference is counted once, at its lower row
-            sT += (double)(gs * r0);                                    // dS/dT = raw
+            r2 = fmaf(dnext, dnext, r2);                                // every difference is counted once, at its lower row
+            rT = fmaf(gs, r0, rT);                                      // dS/dT = raw
             Elt<T>::store(G, k, gs * Tv);
         }
+        s2 += (double)r2; sT += (double)rT;
         a += a_step;
         if (a >= Nq) a -= Nq;
     }
@@ -121,7 +123,7 @@ sparsity_kernel(const void* __restrict__ raw, const float* __restrict__ Tptr, fl
     // (C) softmax backward per row: dS[t,p] = probs[t,p] * (gp[p] - sum_p' probs[t,p'] gp[p'])
     double sT = 0.0;
     for (int t = warp; t < Nq; t += kThreads / 32) {
-        float dot = 0.f;
+        float dot = 0.f, rT = 0.f;
         for (int p = lane; p < Nv; p += 32)
             dot += __expf(Elt<T>::scaled(Elt<T>::load(raw, base + (size_t)t * Nv + p), Tv) - m[t]) * rz[t] * gp[p];
         dot = warp_sum(dot);
@@ -129,9 +131,10 @@ sparsity_kernel(const void* __restrict__ raw, const float* __restrict__ Tptr, fl
             const float r0 = Elt<T>::load(raw, base + (size_t)t * Nv + p);
             const float pr = __expf(Elt<T>::scaled(r0, Tv) - m[t]) * rz[t];
             const float gs = pr * (gp[p] - dot);
-            sT += (double)(gs * r0);
+            rT = fmaf(gs, r0, rT);
             Elt<T>::store(G, base + (size_t)t * Nv + p, gs * Tv);
         }
+        sT += (double)rT;
     }
     block_partials(v2, sT, partials);
 }
@@ -181,7 +184,7 @@ constexpr int kMaxBlocks = 148 * 8;
 using namespace triad;
 
 extern "C" size_t triad_pospair_workspace_bytes(int B) {
-    const int blocks = B > pospair::kMaxBlocks * 4 ? B : pospair::kMaxBlocks * 4;
+    const int blocks = B > pospair::kMaxBlocks ? B : pospair::kMaxBlocks;
     return (size_t)blocks * 2 * sizeof(double);
 }
 
@@ -198,7 +201,7 @@ extern "C" int triad_pospair_terms(const void* raw, int dtype, const float* temp
     double scale0;
     if (mode == 0) {
         if ((long long)B * Nq > 0x7fffffffLL) return fail_msg(TRIAD_ERR_BAD_SHAPE, "pospair_terms: B*Nq overflows int32");
-        blocks = B * Nq < pospair::kMaxBlocks * 4 ? B * Nq : pospair::kMaxBlocks * 4;
+        blocks = B * Nq < pospair::kMaxBlocks ? B * Nq : pospair::kMaxBlocks;
         // mean over B*(Nq-1)*Nv differences; a single token row has none: 0/0 = NaN, like torch.mean of an empty tensor
         scale0 = 1.0 / ((double)B * (double)(Nq - 1) * (double)Nv);
         if (dtype == TRIAD_DTYPE_BF16)
