@@ -63,22 +63,57 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during a timed region (B200_PROFILING.md)."""
+    """SM clock, board power and clock-event (throttle) reasons during a timed region (B200_PROFILING.md's clocks
+    line).  Sampled in-process through NVML every 10 ms (tools/sampler_ab.py: no measurable effect on the step);
+    `nvidia-smi -lms 25` — whose start-up alone takes ~0.1 s, i.e. misses short regions — is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+            ("hw_power_brake", 0x80))
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nv, self.stop = [], None, index, None, False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self):
+        nv, h = self.nv
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop:
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx, nv.nvmlDeviceGetPowerUsage(h) / 1e3]
+                                 + ["Active" if r & bit else "Not Active" for _, bit in self.BITS])
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def __enter__(self):
+        try:
+            self.nv = self._nvml_handle()
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            time.sleep(0.02)                    # the first sample is out before the timed region starts
+            return self
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
-            time.sleep(0.08)                    # the first sample is out before the timed region starts
+            time.sleep(0.08)
         except Exception:
             self.proc = None
         return self
@@ -88,7 +123,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *a):
-        if self.proc is not None:
+        if self.nv is not None:
+            time.sleep(0.02)
+            self.stop = True
+            self.t.join(timeout=1)
+        elif self.proc is not None:
             time.sleep(0.05)
             self.proc.terminate()
             try:
@@ -98,19 +137,20 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, pw, reasons = [], 0.0, [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = [n for n, _ in self.BITS]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1])); pw.append(float(r[2]))
-                for n, val in zip(names, r[3:7]):
-                    if val.lower().startswith("active"):
+                for n, val in zip(names, r[3:3 + len(names)]):
+                    if str(val).lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
-                "sm_mhz_min": min(sm), "power_w_max": max(pw) if pw else None}
+                "sm_mhz_min": min(sm), "power_w_max": max(pw) if pw else None,
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -514,6 +554,8 @@ def run_triad(args, cfg_key):
         model.triad_regularizers = True
         for i in range(2):
             step(*sets[i % n_sets])
+        torch.cuda.synchronize()
+        time.sleep(1.0)                       # every side block starts from an idle GPU, as the headline region does
         k_full = max(3, min(args.steps, 10))
         with ClockSampler(local) as ck:
             full_ms = timed(lambda i: step(*sets[i % n_sets]), k_full)
@@ -534,6 +576,8 @@ def run_triad(args, cfg_key):
                 s[0].requires_grad_(True); s[1].requires_grad_(True)
             for i in range(3):
                 step_single(*s3[i % 3])
+            torch.cuda.synchronize()
+            time.sleep(1.0)
             fwd_ev.clear()
             k3 = max(5, min(args.steps, 20))
             with ClockSampler(local) as ck:
