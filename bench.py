@@ -557,11 +557,27 @@ def run_triad(args, cfg_key):
         torch.cuda.synchronize()
         time.sleep(1.0)                       # every side block starts from an idle GPU, as the headline region does
         k_full = max(3, min(args.steps, 10))
+        # timed like every other block (one pair of events around K steps); in addition every step gets its own event
+        # and the host notes when it had finished queueing it, so a slow step can be told from a late host
+        ev_full = [torch.cuda.Event(enable_timing=True) for _ in range(k_full + 1)]
+        host_t = []
+
+        def full_step(i):
+            if i == 0:
+                ev_full[0].record()
+            t0 = time.perf_counter()
+            step(*sets[i % n_sets])
+            host_t.append((time.perf_counter() - t0) * 1e3)
+            ev_full[i + 1].record()
+
         with ClockSampler(local) as ck:
-            full_ms = timed(lambda i: step(*sets[i % n_sets]), k_full)
+            full_ms = timed(full_step, k_full)
+        per_full = [ev_full[i].elapsed_time(ev_full[i + 1]) for i in range(k_full)]
         model.triad_regularizers = False
         extras["full_loss"] = {
             "value": float(B) * B / (full_ms * 1e-3), "unit": "clip-pairs/s", "ms_per_step": full_ms, "steps": k_full,
+            "per_step_ms": [round(x, 2) for x in per_full], "median_ms": statistics.median(per_full),
+            "host_queue_ms_per_step": [round(x, 2) for x in host_t],
             "clocks": ck.summary(),
             "what": "same step with the reference's regularisers on (model.py:394-428 / :516-542): dense non-negative "
                     "pressure, smoothness / sparsity on the positive pairs; not part of BASELINE.json's metric"}

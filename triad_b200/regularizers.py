@@ -33,9 +33,29 @@ from ._lib import check
 CHUNK_BYTES = 16 << 30
 
 
+#: cudaMemGetInfo is a driver query that can take milliseconds (tens of them while another client — nvidia-smi, an NVML
+#: poller — talks to the driver): asked once per training step it showed up as 10-50 ms host stalls in bench.py's
+#: full-loss block.  The answer is cached per device for this many seconds.
+FREE_MEMORY_TTL_S = 2.0
+_free_cache = {}
+
+
+def _free_bytes(device) -> int:
+    import time
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    now = time.monotonic()
+    hit = _free_cache.get(key)
+    if hit is None or now - hit[0] > FREE_MEMORY_TTL_S:
+        hit = (now, int(torch.cuda.mem_get_info(dev)[0]))
+        _free_cache[key] = hit
+    return hit[1]
+
+
 def chunk_budget(device, chunk_bytes: int) -> int:
-    free, _ = torch.cuda.mem_get_info(device)
-    return max(1 << 20, min(int(chunk_bytes), free // 4)) if chunk_bytes >= (1 << 20) else int(chunk_bytes)
+    if chunk_bytes < (1 << 20):
+        return int(chunk_bytes)
+    return max(1 << 20, min(int(chunk_bytes), _free_bytes(device) // 4))
 
 
 def nonneg_chunk(S: torch.Tensor, T: torch.Tensor, lo: float, coef: float, write_grad: bool,
