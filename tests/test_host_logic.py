@@ -85,3 +85,39 @@ def test_bench_cpu_arm_reports_reference_kind():
     from oracle import ref_loader
     assert kind == ("reference" if ref_loader.available() else "port")
     assert step() == step()                               # deterministic, finite
+
+
+def test_chunk_budget_queries_the_driver_once_per_ttl(monkeypatch):
+    """regularizers.chunk_budget caps a chunk of N at a quarter of the free memory; the driver query behind it
+    (cudaMemGetInfo: milliseconds, more while NVML clients talk to the driver) is cached, not issued per training step."""
+    from triad_b200 import regularizers as R
+    calls = []
+
+    def fake_mem_get_info(device=None):
+        calls.append(device)
+        return (40 << 30, 180 << 30)
+
+    monkeypatch.setattr(torch.cuda, "mem_get_info", fake_mem_get_info)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    R._free_cache.clear()
+    assert R.chunk_budget("cuda:0", 16 << 30) == 10 << 30        # free // 4
+    assert R.chunk_budget("cuda:0", 16 << 30) == 10 << 30
+    assert R.chunk_budget("cuda:0", 4 << 30) == 4 << 30          # the caller's bound when it is the smaller one
+    assert len(calls) == 1
+    assert R.chunk_budget("cuda:0", 4096) == 4096 and len(calls) == 1      # test-sized chunks never ask
+    monkeypatch.setattr(R, "FREE_MEMORY_TTL_S", -1.0)            # expired: asks again
+    R.chunk_budget("cuda:0", 16 << 30)
+    assert len(calls) == 2
+    R._free_cache.clear()
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """bench.ClockSampler never raises: no NVML / no nvidia-smi gives an empty summary (the bench line still prints)."""
+    import bench
+    import time as _t
+    with bench.ClockSampler(0) as c:
+        _t.sleep(0.03)
+    s = c.summary()
+    assert set(s) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+    if s["samples"] == 0:
+        assert s["sm_mhz"] is None and s["reasons"] == []
