@@ -7,10 +7,11 @@ Two kinds of term read the token-similarity tensor the fused path never builds:
   :525-526, lo=-20).  Its gradient is dense (every negative similarity), so its backward is two
   real GEMMs.  ``DenseNonNeg`` streams the batch in image chunks: N = dL/d<q,v> for the chunk comes
   straight out of the tcgen05 forward kernel (``triad_nonneg_fused_chunk``: the epilogue writes
-  coef*T*min(S,0) instead of reducing the tile, and the sums for the value and dL/dT), then two
-  library GEMMs (dQ += N V, dV = N^T Q).  For fp32 inputs / shapes the tensor-core kernel does not
-  take: library GEMM (raw <q,v>) -> ``triad_nonneg_chunk`` (elementwise, in place) -> the same two
-  GEMMs.  Nothing of size B^2*Nq*Nv is ever resident (see DESIGN.md §4 K5 for why the two backward
+  coef*T*min(S,0) instead of reducing the tile, and the sums for the value and dL/dT) — or, in
+  training, out of the SAME pass as the max-mean forward (``triad_maxmean_fwd_nonneg``) — then the
+  two hand-written tcgen05 GEMMs ``triad_dense_grad_gemm`` (dQ = N V, dV = N^T Q; MN-major operands,
+  no transposed copies).  For fp32 inputs / shapes the tensor-core kernels do not take: library GEMM
+  (raw <q,v>) -> ``triad_nonneg_chunk`` (elementwise, in place) -> two library GEMMs.  Nothing of size B^2*Nq*Nv is ever resident (see DESIGN.md §4 K5 for why the two backward
   GEMMs are not fused into a flash-attention-style kernel at D = 512).
 * terms on the B POSITIVE pairs only (token_sims[i,i]): temporal smoothness (model.py:394-408)
   and patch-usage sparsity (:528-541).  They touch B*Nq*Nv elements — 1/B of the tensor:
@@ -19,6 +20,8 @@ Two kinds of term read the token-similarity tensor the fused path never builds:
   batched GEMMs in backward, instead of the ~40 ATen kernels of the reference's autograd graph.
 """
 from __future__ import annotations
+
+import time
 
 import torch
 
@@ -41,7 +44,6 @@ _free_cache = {}
 
 
 def _free_bytes(device) -> int:
-    import time
     dev = torch.device(device)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     now = time.monotonic()
