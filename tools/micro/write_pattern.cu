@@ -1,3 +1,6 @@
+// SUPERSEDED by write_pattern2.cu: this probe's stores fill a 128-byte line with 16 separate 16-byte pieces per warp
+// instruction stream (partial-sector writes), so it measures the store instruction pattern, not the layout (1.8 / 2.2 TB/s
+// here against 5.2 / 6.3 TB/s with full-line stores).
 // Write-bandwidth probe for the dense regulariser's N (8.4 GB at cfg 2): the same bytes written
 //   (a) row-major  N[M][Bv*Nv]   — a CTA owns 128 rows and appends 512 B per row per image (pitch 128 KB): what the
 //       forward's epilogue does;
